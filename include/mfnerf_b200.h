@@ -1,0 +1,105 @@
+/* mfnerf_b200.h -- C ABI of libmfnerf_b200.so, the sm_100a (B200) implementation of MF-NeRF's per-ray /
+ * per-sample hot path.  This is the drop-in boundary that replaces the reference's pybind11 module `vren`
+ * (models/csrc/binding.cpp:234-251) and the tiny-cuda-nn calls of models/networks.py:36-94.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in `_host`;
+ *   - the library never allocates user-visible memory: outputs and workspaces are passed in
+ *     (query *_workspace_bytes first); nothing is zero-filled by the caller unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no call synchronises;
+ *   - return value: 0 on success, <0 on error (MFN_ERR_*), text via mfn_last_error() (thread-local);
+ *   - set MFN_DEBUG_SYNC=1 to synchronise and check after every launch.
+ * Layouts are the reference's: row-major contiguous, (N,3) float triples, rays_a = (R,3) int64
+ * {ray_idx, start_idx, N_samples}.
+ */
+#ifndef MFNERF_B200_H_
+#define MFNERF_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFN_VERSION 100
+
+#define MFN_DTYPE_F32 0
+#define MFN_DTYPE_F16 1
+#define MFN_DTYPE_F64 2
+
+int mfn_version(void);
+const char* mfn_last_error(void);
+/* compute capability of the current device as major*10+minor (100 on B200), -1 without a device */
+int mfn_device_arch(void);
+
+/* ---- grid utilities -------------------------------------------------------------------------------- */
+/* replaces vren.morton3D  (binding.cpp:47-51 -> raymarching.cu:62-87): coords (n,3) int32 -> indices (n) int32 */
+int mfn_morton3d(const int32_t* coords, int64_t n, int32_t* indices, void* stream);
+/* replaces vren.morton3D_invert (binding.cpp:54-58 -> raymarching.cu:90-119): indices (n) -> coords (n,3) */
+int mfn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, void* stream);
+/* replaces vren.packbits (binding.cpp:35-44 -> raymarching.cu:122-161): bit i of byte k = grid[8k+i] > thr.
+ * grid holds 8*n_bytes elements of `dtype` (MFN_DTYPE_*). */
+int mfn_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold, uint8_t* density_bitfield, void* stream);
+
+/* ---- intersection ---------------------------------------------------------------------------------- */
+/* replaces vren.ray_aabb_intersect (binding.cpp:4-16 -> intersection.cu:59-100).
+ * hit_cnt (n_rays) int32, hits_t (n_rays,max_hits,2) f32 (-1 = no hit), hits_voxel_idx (n_rays,max_hits) int64.
+ * Rows are sorted by t1 ascending exactly like the reference's sort (so -1 padding comes first). */
+int mfn_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* half_sizes,
+                           int64_t n_rays, int64_t n_voxels, int max_hits, int32_t* hit_cnt, float* hits_t,
+                           int64_t* hits_voxel_idx, void* stream);
+/* replaces vren.ray_sphere_intersect (binding.cpp:19-32 -> intersection.cu:156-197) */
+int mfn_ray_sphere_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* radii,
+                             int64_t n_rays, int64_t n_spheres, int max_hits, int32_t* hit_cnt, float* hits_t,
+                             int64_t* hits_sphere_idx, void* stream);
+
+/* ---- ray marching ---------------------------------------------------------------------------------- */
+/* replaces vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:166-332), split so the caller can size
+ * the sample arrays exactly: _count fills rays_a (n_rays,3) int64 and counter (2) int32 = {total samples,
+ * n_rays}; _write then emits exactly the samples (rows < capacity).  mfn_raymarching_train = both. */
+int64_t mfn_march_train_workspace_bytes(int64_t n_rays, int max_samples);
+int mfn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* density_bitfield,
+                          int cascades, float scale, float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                          int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace, int64_t workspace_bytes, void* stream);
+int mfn_march_train_write(const float* rays_o, const float* rays_d, const int64_t* rays_a, const void* workspace, int max_samples,
+                          int64_t n_rays, int64_t capacity, float* xyzs, float* dirs, float* deltas, float* ts, void* stream);
+int mfn_raymarching_train(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* density_bitfield,
+                          int cascades, float scale, float exp_step_factor, const float* noise, int grid_size, int max_samples,
+                          int64_t n_rays, int64_t capacity, int64_t* rays_a, float* xyzs, float* dirs, float* deltas, float* ts,
+                          int32_t* counter, void* workspace, int64_t workspace_bytes, void* stream);
+/* replaces vren.raymarching_test (binding.cpp:84-107 -> raymarching.cu:335-454).  hits_t (n_rays_total,2) is
+ * advanced in place; xyzs/dirs (n_alive,n_samples,3), deltas/ts (n_alive,n_samples) are fully written
+ * (zero padded); n_eff_samples (n_alive) int32. */
+int mfn_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,
+                         const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor, int grid_size,
+                         int max_samples, int n_samples, int64_t n_alive, float* xyzs, float* dirs, float* deltas, float* ts,
+                         int32_t* n_eff_samples, void* stream);
+
+/* ---- compositing ----------------------------------------------------------------------------------- */
+/* replaces vren.composite_train_fw (binding.cpp:110-127 -> volumerendering.cu:6-84).  All outputs fully written. */
+int mfn_composite_train_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts, const int64_t* rays_a,
+                           float T_threshold, int64_t n_rays, int64_t n_samples, int64_t* total_samples, float* opacity,
+                           float* depth, float* rgb, float* ws, void* stream);
+/* replaces vren.composite_train_bw (binding.cpp:130-167 -> volumerendering.cu:87-202) */
+int mfn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,
+                           const float* sigmas, const float* rgbs, const float* ws, const float* deltas, const float* ts,
+                           const int64_t* rays_a, const float* opacity, const float* depth, const float* rgb, float T_threshold,
+                           int64_t n_rays, int64_t n_samples, float* dL_dsigmas, float* dL_drgbs, void* stream);
+/* replaces vren.composite_test_fw (binding.cpp:170-198 -> volumerendering.cu:205-285).  opacity/depth/rgb and
+ * alive_indices are updated in place; sigmas/deltas/ts (n_alive,n_samples), rgbs (n_alive,n_samples,3). */
+int mfn_composite_test_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts, int64_t* alive_indices,
+                          float T_threshold, const int32_t* n_eff_samples, int n_samples, int64_t n_alive, float* opacity,
+                          float* depth, float* rgb, void* stream);
+
+/* ---- distortion loss ------------------------------------------------------------------------------- */
+/* replaces vren.distortion_loss_fw (binding.cpp:201-213 -> losses.cu:64-109) */
+int mfn_distortion_loss_fw(const float* ws, const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays,
+                           int64_t n_samples, float* loss, float* ws_inclusive_scan, float* wts_inclusive_scan, void* stream);
+/* replaces vren.distortion_loss_bw (binding.cpp:216-231 -> losses.cu:145-175) */
+int mfn_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan, const float* ws,
+                           const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays, int64_t n_samples,
+                           float* dL_dws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFNERF_B200_H_ */

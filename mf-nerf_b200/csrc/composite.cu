@@ -1,0 +1,214 @@
+// Transmittance compositing, forward / backward / test-time  (ref: models/csrc/volumerendering.cu)
+//
+// Train kernels: one warp per rays_a row; lanes stride over the ray's samples so every global access is
+// coalesced (the reference walks each ray with a single thread).  The transmittance recurrence
+// T_{s+1} = T_s * (1 - a_s) is replayed in the reference's exact sequential order (each lane runs the same
+// 32-step chain from shuffled alphas) so ws = a*T and the early-termination index are bit-identical given
+// identical inputs; the per-ray sums (rgb, depth, opacity) use a warp tree and therefore agree with the
+// reference's sequential fp32 accumulation only to rounding (tolerance stated in tests/).
+// Algorithmic bytes: fw 28 B/sample + 52 B/ray, bw 48 B/sample + 64 B/ray.
+#include "common.cuh"
+#include "../../include/mfnerf_b200.h"
+
+namespace mfn {
+
+constexpr int kCompWarps = 8;
+
+// alpha exactly as the reference computes it: 1 - __expf(-sigma*delta)  (volumerendering.cu:30)
+__device__ __forceinline__ float alpha_of(float sigma, float delta) { return __fadd_rn(1.0f, -__expf(-__fmul_rn(sigma, delta))); }
+
+// Sequential transmittance over one 32-sample chunk.  Returns T before this lane's sample; *t_end is T
+// after the whole chunk (identical in all lanes).
+__device__ __forceinline__ float chunk_transmittance(float a, float T_in, int lane, float* t_end) {
+    float Tj = T_in, mine = T_in;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float aj = __shfl_sync(0xffffffffu, a, j);
+        if (j == lane) mine = Tj;
+        Tj = __fmul_rn(Tj, __fadd_rn(1.0f, -aj));
+    }
+    *t_end = Tj;
+    return mine;
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                          const float* __restrict__ ts, const int64_t* __restrict__ rays_a, float T_thr, int64_t n_rows,
+                          int64_t* __restrict__ total_samples, float* __restrict__ opacity, float* __restrict__ depth,
+                          float* __restrict__ rgb, float* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t ray = rays_a[3 * row], start = rays_a[3 * row + 1];
+    const int n = (int)rays_a[3 * row + 2];
+    float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
+    int samples = n;
+    int base = 0;
+    for (; base < n; base += 32) {
+        const int s = base + lane;
+        const bool valid = s < n;
+        const int64_t g = start + s;
+        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) {
+            a = alpha_of(sigmas[g], deltas[g]);
+            t = ts[g]; cr = rgbs[3 * g]; cg = rgbs[3 * g + 1]; cb = rgbs[3 * g + 2];
+        }
+        float T_end;
+        const float T_mine = chunk_transmittance(a, T, lane, &T_end);
+        const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));
+        const uint32_t stop = __ballot_sync(0xffffffffu, valid && T_after <= T_thr);  // l.41
+        const int last = stop ? (__ffs(stop) - 1) : 31;
+        const bool in = valid && lane <= last;
+        const float w = in ? __fmul_rn(a, T_mine) : 0.f;
+        if (valid) ws[g] = w;
+        acc_r += w * cr; acc_g += w * cg; acc_b += w * cb; acc_d += w * t; acc_o += w;
+        T = T_end;
+        if (stop) { samples = base + last; base += 32; break; }
+    }
+    for (int s = base + lane; s < n; s += 32) ws[start + s] = 0.f;  // samples behind an early stop keep w = 0
+    acc_r = warp_sum(acc_r); acc_g = warp_sum(acc_g); acc_b = warp_sum(acc_b); acc_d = warp_sum(acc_d); acc_o = warp_sum(acc_o);
+    if (lane == 0) {
+        total_samples[ray] = samples;
+        opacity[ray] = acc_o; depth[ray] = acc_d;
+        rgb[3 * ray] = acc_r; rgb[3 * ray + 1] = acc_g; rgb[3 * ray + 2] = acc_b;
+    }
+}
+
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __restrict__ dL_ddepth, const float* __restrict__ dL_drgb,
+                          const float* __restrict__ dL_dws, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                          const float* __restrict__ ws, const float* __restrict__ deltas, const float* __restrict__ ts,
+                          const int64_t* __restrict__ rays_a, const float* __restrict__ opacity, const float* __restrict__ depth,
+                          const float* __restrict__ rgb, float T_thr, int64_t n_rows, float* __restrict__ dL_dsigmas,
+                          float* __restrict__ dL_drgbs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int64_t ray = rays_a[3 * row], start = rays_a[3 * row + 1];
+    const int n = (int)rays_a[3 * row + 2];
+    if (n == 0) return;
+    // sum over the ray of dL/dw * w  (the reference builds it with an in-place inclusive scan, l.119-123)
+    float wsum = 0.f;
+    for (int s = lane; s < n; s += 32) wsum += dL_dws[start + s] * ws[start + s];
+    wsum = warp_sum(wsum);
+    const float R = rgb[3 * ray], G = rgb[3 * ray + 1], B = rgb[3 * ray + 2], O = opacity[ray], D = depth[ray];
+    const float gR = dL_drgb[3 * ray], gG = dL_drgb[3 * ray + 1], gB = dL_drgb[3 * ray + 2];
+    const float gO = dL_dopacity[ray], gD = dL_ddepth[ray];
+    float T = 1.0f, cr_run = 0.f, cg_run = 0.f, cb_run = 0.f, d_run = 0.f, p_run = 0.f;
+    int base = 0;
+    for (; base < n; base += 32) {
+        const int s = base + lane;
+        const bool valid = s < n;
+        const int64_t g = start + s;
+        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dl = 0.f, gw = 0.f, wsv = 0.f;
+        if (valid) {
+            dl = deltas[g];
+            a = alpha_of(sigmas[g], dl);
+            t = ts[g]; cr = rgbs[3 * g]; cg = rgbs[3 * g + 1]; cb = rgbs[3 * g + 2];
+            gw = dL_dws[g]; wsv = ws[g];
+        }
+        float T_end;
+        const float T_mine = chunk_transmittance(a, T, lane, &T_end);
+        const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));
+        const uint32_t stop = __ballot_sync(0xffffffffu, valid && T_after <= T_thr);  // l.148
+        const int last = stop ? (__ffs(stop) - 1) : 31;
+        const bool in = valid && lane <= last;
+        const float w = valid ? __fmul_rn(a, T_mine) : 0.f;
+        // inclusive running sums along the ray (r, g, b, d of l.131-132 and the dL_dws*ws prefix of l.119)
+        const float r_in = cr_run + warp_incl_scan(w * cr, lane);
+        const float g_in = cg_run + warp_incl_scan(w * cg, lane);
+        const float b_in = cb_run + warp_incl_scan(w * cb, lane);
+        const float d_in = d_run + warp_incl_scan(w * t, lane);
+        const float p_in = p_run + warp_incl_scan(gw * wsv, lane);
+        if (valid) {
+            float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+            if (in) {
+                dr = gR * w; dg = gG * w; db = gB * w;
+                ds = dl * (gR * (cr * T_after - (R - r_in)) + gG * (cg * T_after - (G - g_in)) + gB * (cb * T_after - (B - b_in)) +
+                           gO * (1.0f - O) + gD * (t * T_after - (D - d_in)) + T_after * gw - (wsum - p_in));
+            }
+            dL_dsigmas[g] = ds;
+            dL_drgbs[3 * g] = dr; dL_drgbs[3 * g + 1] = dg; dL_drgbs[3 * g + 2] = db;
+        }
+        cr_run = __shfl_sync(0xffffffffu, r_in, 31); cg_run = __shfl_sync(0xffffffffu, g_in, 31);
+        cb_run = __shfl_sync(0xffffffffu, b_in, 31); d_run = __shfl_sync(0xffffffffu, d_in, 31);
+        p_run = __shfl_sync(0xffffffffu, p_in, 31);
+        T = T_end;
+        if (stop) { base += 32; break; }
+    }
+    for (int s = base + lane; s < n; s += 32) {
+        const int64_t g = start + s;
+        dL_dsigmas[g] = 0.f; dL_drgbs[3 * g] = 0.f; dL_drgbs[3 * g + 1] = 0.f; dL_drgbs[3 * g + 2] = 0.f;
+    }
+}
+
+// test-time compositor: one thread per alive ray, the reference's sequential order (so opacity / depth /
+// rgb are bit-identical to the reference given identical inputs).  (ref: volumerendering.cu:219-248)
+__global__ void composite_test_fw_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                         const float* __restrict__ ts, int64_t* __restrict__ alive, float T_thr,
+                                         const int32_t* __restrict__ n_eff, int n_samples, int64_t n_alive,
+                                         float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int ne = n_eff[n];
+    if (ne == 0) { alive[n] = -1; return; }
+    const int64_t r = alive[n];
+    float o = opacity[r], d = depth[r], cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
+    float T = __fadd_rn(1.0f, -o);
+    const int64_t rowb = n * (int64_t)n_samples;
+    for (int s = 0; s < ne; ++s) {
+        const float a = alpha_of(sigmas[rowb + s], deltas[rowb + s]);
+        const float w = __fmul_rn(a, T);
+        cr = __fmaf_rn(w, rgbs[3 * (rowb + s)], cr);
+        cg = __fmaf_rn(w, rgbs[3 * (rowb + s) + 1], cg);
+        cb = __fmaf_rn(w, rgbs[3 * (rowb + s) + 2], cb);
+        d = __fmaf_rn(w, ts[rowb + s], d);
+        o = __fadd_rn(o, w);
+        T = __fmul_rn(T, __fadd_rn(1.0f, -a));
+        if (T <= T_thr) { alive[n] = -1; break; }
+    }
+    opacity[r] = o; depth[r] = d; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+}
+
+}  // namespace mfn
+
+using namespace mfn;
+
+extern "C" int mfn_composite_train_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts, const int64_t* rays_a,
+                                      float T_threshold, int64_t n_rays, int64_t n_samples, int64_t* total_samples, float* opacity,
+                                      float* depth, float* rgb, float* ws, void* stream) {
+    (void)n_samples;
+    if (n_rays < 0) { set_error("mfn_composite_train_fw: bad argument"); return MFN_ERR_ARG; }
+    if (n_rays == 0) return MFN_OK;
+    if (!rays_a || !total_samples || !opacity || !depth || !rgb) { set_error("mfn_composite_train_fw: null pointer"); return MFN_ERR_ARG; }
+    composite_train_fw_kernel<<<(int)ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, rays_a, T_threshold, n_rays, total_samples, opacity, depth, rgb, ws);
+    return check_launch("mfn_composite_train_fw", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_composite_train_bw(const float* dL_dopacity, const float* dL_ddepth, const float* dL_drgb, const float* dL_dws,
+                                      const float* sigmas, const float* rgbs, const float* ws, const float* deltas, const float* ts,
+                                      const int64_t* rays_a, const float* opacity, const float* depth, const float* rgb,
+                                      float T_threshold, int64_t n_rays, int64_t n_samples, float* dL_dsigmas, float* dL_drgbs,
+                                      void* stream) {
+    (void)n_samples;
+    if (n_rays < 0) { set_error("mfn_composite_train_bw: bad argument"); return MFN_ERR_ARG; }
+    if (n_rays == 0) return MFN_OK;
+    if (!rays_a || !dL_dopacity || !dL_ddepth || !dL_drgb || !opacity || !depth || !rgb) { set_error("mfn_composite_train_bw: null pointer"); return MFN_ERR_ARG; }
+    composite_train_bw_kernel<<<(int)ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+        dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth, rgb, T_threshold, n_rays,
+        dL_dsigmas, dL_drgbs);
+    return check_launch("mfn_composite_train_bw", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_composite_test_fw(const float* sigmas, const float* rgbs, const float* deltas, const float* ts,
+                                     int64_t* alive_indices, float T_threshold, const int32_t* n_eff_samples, int n_samples,
+                                     int64_t n_alive, float* opacity, float* depth, float* rgb, void* stream) {
+    if (n_alive < 0 || n_samples < 0) { set_error("mfn_composite_test_fw: bad argument"); return MFN_ERR_ARG; }
+    if (n_alive == 0) return MFN_OK;
+    if (!alive_indices || !n_eff_samples || !opacity || !depth || !rgb) { set_error("mfn_composite_test_fw: null pointer"); return MFN_ERR_ARG; }
+    const int threads = 128;
+    composite_test_fw_kernel<<<(int)ceil_div(n_alive, threads), threads, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff_samples, n_samples, n_alive, opacity, depth, rgb);
+    return check_launch("mfn_composite_test_fw", (cudaStream_t)stream);
+}

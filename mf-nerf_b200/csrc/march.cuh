@@ -1,0 +1,198 @@
+// Occupancy-bitfield ray marching, shared device code  (ref: models/csrc/raymarching.cu:7-32, 166-279, 335-404)
+//
+// Bit-exactness contract.  N_samples, ts, deltas and xyzs must equal the reference's to the last bit, so
+// every fp32 operation below is spelled with a round-to-nearest intrinsic that nvcc can neither contract
+// nor re-associate, in exactly the shape the reference's own SASS has when built with its stock flags
+// (-O2, -fmad=true, -prec-div=true; checked with cuobjdump on oracle/_ref/vren_ref*.so):
+//     x        = fma(d, t, o)                               (raymarching.cu:205)
+//     dt       = max(dt_min, min(t*esf, dt_max))            (helper_math clamp; raymarching.cu:11-13)
+//     cell     = trunc(max(0, min(fma(x, 1/bound, 1)*0.5*G, G-1)))            (l.215-217)
+//     t_exit_x = fma(bound, fma((n+0.5 + 0.5*sign)*(1/G), 2, -1), -x) * (1/d) (l.225)
+//     t_next   = dt + t                                     (l.222, l.231)
+// Key structural fact used by the warp marcher: both the "occupied" step and the "skip" loop advance t
+// with the same map t -> t + dt(t), so the sequence of candidate positions along a ray (the "lattice")
+// does not depend on occupancy.  32 lanes evaluate 32 consecutive lattice points at once and the
+// sequential visit order of the reference is then replayed with ballots.
+#pragma once
+#include "common.cuh"
+
+namespace mfn {
+
+struct MarchConst {
+    float dt_min, dt_max, esf;
+    float gs, gs_inv, gsm1;   // (float)G, 1/G, G-1
+    float scale;              // mip_bound clamp
+    int cascades, grid_size;
+    uint32_t g3;
+};
+
+// `dt_scale` is `scale` for the train marcher and (float)cascades for the test marcher -- the reference
+// passes `cascades` to calc_dt in raymarching_test_kernel (raymarching.cu:370,399), a quirk we keep.
+__device__ __forceinline__ MarchConst make_march_const(int cascades, int grid_size, float scale, float esf, int max_samples, float dt_scale) {
+    MarchConst c;
+    c.esf = esf;
+    c.dt_min = __fdiv_rn(1.73205080757f, (float)max_samples);
+    c.dt_max = __fdiv_rn(__fmul_rn(dt_scale, 3.4641015529632568359f), (float)grid_size);
+    c.gs = (float)grid_size;
+    c.gs_inv = __fdiv_rn(1.0f, c.gs);
+    c.gsm1 = __fadd_rn(c.gs, -1.0f);
+    c.scale = scale;
+    c.cascades = cascades;
+    c.grid_size = grid_size;
+    c.g3 = (uint32_t)grid_size * grid_size * grid_size;
+    return c;
+}
+
+__device__ __forceinline__ float march_dt(float t, const MarchConst& c) {
+    return fmaxf(fminf(__fmul_rn(t, c.esf), c.dt_max), c.dt_min);
+}
+__device__ __forceinline__ float march_next(float t, const MarchConst& c) { return __fadd_rn(march_dt(t, c), t); }
+
+struct RayConst {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz, sx, sy, sz;
+};
+__device__ __forceinline__ RayConst make_ray(const float* __restrict__ o, const float* __restrict__ d, int64_t r) {
+    RayConst q;
+    q.ox = o[3 * r]; q.oy = o[3 * r + 1]; q.oz = o[3 * r + 2];
+    q.dx = d[3 * r]; q.dy = d[3 * r + 1]; q.dz = d[3 * r + 2];
+    q.ix = __fdiv_rn(1.0f, q.dx); q.iy = __fdiv_rn(1.0f, q.dy); q.iz = __fdiv_rn(1.0f, q.dz);
+    q.sx = copysignf(1.0f, q.dx); q.sy = copysignf(1.0f, q.dy); q.sz = copysignf(1.0f, q.dz);
+    return q;
+}
+
+struct Probe {
+    float x, y, z, dt, t_target;
+    bool occ;
+};
+
+// Evaluate one lattice point: position, step, cascade, cell, occupancy bit and (if empty) the t at which
+// the ray leaves the cell.  (ref: raymarching.cu:205-228)
+__device__ __forceinline__ Probe probe_cell(float t, const RayConst& q, const MarchConst& c, const uint8_t* __restrict__ bitfield) {
+    Probe p;
+    p.x = __fmaf_rn(q.dx, t, q.ox); p.y = __fmaf_rn(q.dy, t, q.oy); p.z = __fmaf_rn(q.dz, t, q.oz);
+    p.dt = march_dt(t, c);
+    int e_pos, e_dt;
+    (void)frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &e_pos);
+    (void)frexpf(__fmul_rn(p.dt, c.gs), &e_dt);
+    const int mip_pos = min(c.cascades - 1, max(0, e_pos + 1));
+    const int mip_dt = min(c.cascades - 1, max(0, e_dt));
+    const int mip = max(mip_pos, mip_dt);
+    const float bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
+    const float bound_inv = __fdiv_rn(1.0f, bound);
+    const float fx = __fmul_rn(__fmul_rn(__fmaf_rn(p.x, bound_inv, 1.0f), 0.5f), c.gs);
+    const float fy = __fmul_rn(__fmul_rn(__fmaf_rn(p.y, bound_inv, 1.0f), 0.5f), c.gs);
+    const float fz = __fmul_rn(__fmul_rn(__fmaf_rn(p.z, bound_inv, 1.0f), 0.5f), c.gs);
+    const int nx = (int)fmaxf(0.0f, fminf(fx, c.gsm1));
+    const int ny = (int)fmaxf(0.0f, fminf(fy, c.gsm1));
+    const int nz = (int)fmaxf(0.0f, fminf(fz, c.gsm1));
+    const uint32_t idx = (uint32_t)mip * c.g3 + morton_encode((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    p.occ = (__ldg(bitfield + (idx >> 3)) >> (idx & 7u)) & 1u;
+    const float ax = __fmaf_rn(q.sx, 0.5f, __fadd_rn((float)nx, 0.5f));
+    const float ay = __fmaf_rn(q.sy, 0.5f, __fadd_rn((float)ny, 0.5f));
+    const float az = __fmaf_rn(q.sz, 0.5f, __fadd_rn((float)nz, 0.5f));
+    const float tx = __fmul_rn(__fmaf_rn(bound, __fmaf_rn(__fmul_rn(ax, c.gs_inv), 2.0f, -1.0f), -p.x), q.ix);
+    const float ty = __fmul_rn(__fmaf_rn(bound, __fmaf_rn(__fmul_rn(ay, c.gs_inv), 2.0f, -1.0f), -p.y), q.iy);
+    const float tz = __fmul_rn(__fmaf_rn(bound, __fmaf_rn(__fmul_rn(az, c.gs_inv), 2.0f, -1.0f), -p.z), q.iz);
+    p.t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Warp marcher.  One warp walks one ray; `emit(rank, t, dt)` is called by the lane that owns an accepted
+// sample, rank = its index along the ray.  Stops after `max_emit` samples or when t leaves [0, t2).
+// Returns (warp-uniform) the number of samples emitted; *t_after = t following the last emitted sample.
+// ---------------------------------------------------------------------------------------------------
+template <typename Emit>
+__device__ __forceinline__ int march_ray_warp(float t_start, float t2, int max_emit, const RayConst& q, const MarchConst& c,
+                                              const uint8_t* __restrict__ bitfield, int lane, Emit emit, float* t_after) {
+    int n = 0;
+    float t_base = t_start;
+    float pending = -INFINITY;  // skip target carried over from the previous batch
+    float t_last = t_start;
+    // (ref loop condition: 0<=t && t<t2 && N_samples<max_samples, raymarching.cu:204)
+    while (t_base >= 0.0f && t_base < t2 && n < max_emit) {
+        // the lattice: every lane walks the same 32-step chain and keeps its own element
+        float tt = t_base, my_t = t_base;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j == lane) my_t = tt;
+            tt = march_next(tt, c);
+        }
+        const bool active = my_t < t2;
+        Probe p;
+        p.occ = false; p.t_target = 0.f; p.dt = 0.f;
+        if (active) p = probe_cell(my_t, q, c, bitfield);
+        const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+        const uint32_t occ_mask = __ballot_sync(0xffffffffu, active && p.occ);
+        // first lattice point of this batch that the sequential marcher would visit
+        int cur = 0;
+        if (pending > -INFINITY) {
+            const uint32_t m = __ballot_sync(0xffffffffu, my_t >= pending);
+            cur = m ? (__ffs(m) - 1) : 32;
+            if (cur < 32) pending = -INFINITY;
+        }
+        uint32_t take = 0;
+        bool finished = false;
+        while (cur < 32) {
+            if (!((act_mask >> cur) & 1u)) { finished = true; break; }  // t >= t2: ray left the box
+            if ((occ_mask >> cur) & 1u) {
+                const uint32_t rest = ~(occ_mask >> cur);               // run of consecutive occupied points
+                const int run = rest ? (__ffs(rest) - 1) : 32;
+                take |= (run >= 32 ? 0xffffffffu : ((1u << run) - 1u)) << cur;
+                cur += run;
+            } else {
+                const float tgt = __shfl_sync(0xffffffffu, p.t_target, cur);
+                const uint32_t later = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
+                const uint32_t m = __ballot_sync(0xffffffffu, my_t >= tgt) & later;
+                if (m) cur = __ffs(m) - 1;
+                else { pending = tgt; cur = 32; }
+            }
+        }
+        int cnt = __popc(take);
+        if (n + cnt >= max_emit) {  // sample budget reached inside this batch: keep the first ones only
+            const int keep = max_emit - n;
+            if (cnt > keep) {
+                uint32_t m = take;  // drop the lowest keep-1 set bits; what is left starts at the keep-th one
+                for (int i = 1; i < keep; ++i) m &= m - 1;
+                const int last = __ffs(m) - 1;
+                take &= (last >= 31) ? 0xffffffffu : ((1u << (last + 1)) - 1u);
+                cnt = keep;
+            }
+            finished = true;
+        }
+        if ((take >> lane) & 1u) emit(n + __popc(take & ((1u << lane) - 1u)), my_t, p.dt);
+        if (cnt > 0) {
+            const int last_lane = 31 - __clz(take);
+            t_last = __shfl_sync(0xffffffffu, __fadd_rn(p.dt, my_t), last_lane);
+        }
+        n += cnt;
+        if (finished) break;
+        t_base = tt;
+    }
+    *t_after = t_last;
+    return n;
+}
+
+// Sequential marcher (one thread per ray) -- the reference's own control flow; used by the test-time
+// marcher where each call only asks for a handful of samples per ray.
+template <typename Emit>
+__device__ __forceinline__ int march_ray_thread(float t, float t2, int max_emit, const RayConst& q, const MarchConst& c,
+                                                const uint8_t* __restrict__ bitfield, Emit emit, float* t_after) {
+    int s = 0;
+    float t_last = t;
+    while (t < t2 && s < max_emit) {
+        const Probe p = probe_cell(t, q, c, bitfield);
+        if (p.occ) {
+            emit(s, t, p.dt, p.x, p.y, p.z);
+            t = __fadd_rn(p.dt, t);
+            t_last = t;
+            ++s;
+        } else {
+            do { t = march_next(t, c); } while (t < p.t_target);
+        }
+    }
+    *t_after = t_last;
+    return s;
+}
+
+}  // namespace mfn
