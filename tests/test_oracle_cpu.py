@@ -1,0 +1,153 @@
+"""CPU tests of the oracle itself (oracle/vren_oracle.c): mathematical identities, an independent fp64 torch
+re-derivation of the compositor / distortion gradients, and -- the pin -- the committed outputs of the reference's
+own CUDA kernels (tests/golden/vren_ref_*.npz, produced on a B200 by tests/golden/make_golden_vren.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+import vren_cases as vc
+from oracle import vren_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_morton_roundtrip_and_definition():
+    rng = np.random.RandomState(0)
+    c = rng.randint(0, 1024, (5000, 3)).astype(np.int32)
+    m = orc.morton3D(c)
+    want = np.zeros(5000, np.int64)
+    for b in range(10):
+        for a in range(3):
+            want |= ((c[:, a].astype(np.int64) >> b) & 1) << (3 * b + a)
+    assert np.array_equal(m.astype(np.int64), want)
+    assert np.array_equal(orc.morton3D_invert(m), c)
+
+
+def test_packbits_matches_numpy_little_endian():
+    rng = np.random.RandomState(1)
+    g = rng.randn(8 * 1000).astype(np.float32); g[:4] = [0.3, np.nan, np.inf, 0.30000001]
+    out = np.zeros(1000, np.uint8)
+    orc.packbits(g, 0.3, out)
+    assert np.array_equal(out, np.packbits(g > np.float32(0.3), bitorder="little"))
+
+
+@pytest.mark.parametrize("name", ["lego", "full", "unbounded", "axis"])
+def test_marcher_invariants(name):
+    sc = scenes.scene(name, 512, seed=4)
+    o = vc.run_oracle(sc)
+    ra, ts, dl, xyz = o["rays_a"], o["ts"], o["deltas"], o["xyzs"]
+    assert np.array_equal(ra[:, 0], np.arange(512)) and ra[0, 1] == 0
+    assert np.array_equal(ra[1:, 1], np.cumsum(ra[:-1, 2])) and o["counter"][0] == ra[:, 2].sum() == ts.shape[0]
+    assert ra[:, 2].max() <= sc["max_samples"]
+    ray_of = np.repeat(ra[:, 0], ra[:, 2])
+    h = o["hits_t"]
+    assert (ts >= h[ray_of, 0] - 1e-6).all() and (ts < h[ray_of, 1]).all()
+    same = ray_of[1:] == ray_of[:-1]
+    assert (np.diff(ts)[same] > 0).all()                       # t strictly increases along a ray
+    assert (np.diff(ts)[same] >= dl[:-1][same] * 0.999).all()   # and by at least the previous step
+    np.testing.assert_allclose(xyz, sc["rays_o"][ray_of] + ts[:, None] * sc["rays_d"][ray_of], rtol=0, atol=2e-6 * max(1, sc["scale"]))
+    # every emitted sample sits in an occupied cell of its cascade (independent numpy re-derivation, l.208-220)
+    G, C, scale = sc["grid_size"], sc["cascades"], sc["scale"]
+    mx = np.abs(xyz).max(1)
+    mip_pos = np.clip(np.frexp(mx)[1] + 1, 0, C - 1)
+    mip_dt = np.clip(np.frexp(dl * np.float32(G))[1], 0, C - 1)
+    mip = np.maximum(mip_pos, mip_dt)
+    bound = np.minimum(np.ldexp(np.float32(1), mip - 1), np.float32(scale)).astype(np.float32)
+    cell = np.clip((0.5 * (xyz / bound[:, None] + 1) * G), 0, G - 1).astype(np.int64)
+    m = orc.morton3D(cell.astype(np.int32)).astype(np.int64) + mip * G ** 3
+    occ = (sc["bitfield"][m // 8] >> (m % 8)) & 1
+    assert occ.mean() > 0.999  # cell index re-derived in float64-free numpy may differ on exact cell borders
+    if name == "full":  # dense grid: a sample at every lattice point
+        n_expect = np.floor((h[:, 1] - np.maximum(h[:, 0], 0)) / dl.max())
+        hit = h[:, 0] >= 0
+        assert (np.abs(ra[hit, 2] - n_expect[hit]) <= 2).all()
+    assert (ra[h[:, 0] < 0, 2] == 0).all()
+
+
+def _torch_composite(sig, rgbs, dl, ts, T_thr):
+    """independent fp64 re-derivation for ONE ray: weights with early termination as a constant mask"""
+    a = 1 - torch.exp(-sig * dl)
+    T_after = torch.cumprod(1 - a, 0)
+    T_before = torch.cat([torch.ones(1, dtype=sig.dtype), T_after[:-1]])
+    stop = torch.nonzero(T_after <= T_thr)
+    keep = torch.ones_like(a)
+    if len(stop):
+        keep[stop[0, 0] + 1:] = 0
+    w = a * T_before * keep
+    return w, (w[:, None] * rgbs).sum(0), (w * ts).sum(), w.sum()
+
+
+@pytest.mark.parametrize("name", ["lego", "full"])
+def test_composite_identities_and_gradients(name):
+    sc = scenes.scene(name, 96, seed=6)
+    o = vc.run_oracle(sc)
+    ra, ts, dl = o["rays_a"], o["ts"], o["deltas"]
+    sig, rgbs = scenes.field_values(ts.shape[0], seed=5)
+    # sum of the weights along a ray is its opacity (volumerendering.cu:35-37)
+    np.testing.assert_allclose(np.array([o["cf_ws"][s:s + n].sum() for _, s, n in ra]), o["cf_opacity"], rtol=1e-5, atol=1e-6)
+    gO, gD, gRGB, gW, gL = vc.grads(96, ts.shape[0])
+    checked = 0
+    for r, s, n in ra:
+        if n == 0:
+            assert o["cf_total"][r] == 0 and o["cf_opacity"][r] == 0
+            continue
+        sl = slice(s, s + n)
+        sg = torch.tensor(sig[sl], dtype=torch.float64, requires_grad=True); cl = torch.tensor(rgbs[sl], dtype=torch.float64, requires_grad=True)
+        w, rgb, depth, op = _torch_composite(sg, cl, torch.tensor(dl[sl], dtype=torch.float64), torch.tensor(ts[sl], dtype=torch.float64), 1e-4)
+        np.testing.assert_allclose(o["cf_ws"][sl], w.detach().numpy(), rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(o["cf_rgb"][r], rgb.detach().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(o["cf_depth"][r], depth.item(), rtol=1e-4, atol=1e-6)
+        n_kept = int((w > 0).sum()) if (w == 0).any() else n
+        assert o["cf_total"][r] in (n_kept - 1, n_kept, n) or abs(o["cf_total"][r] - n_kept) <= 1
+        loss = (torch.tensor(gRGB[r], dtype=torch.float64) * rgb).sum() + gD[r] * depth + gO[r] * op + (torch.tensor(gW[sl], dtype=torch.float64) * w).sum()
+        loss.backward()
+        scale = np.abs(sg.grad.numpy()).max() + 1e-6
+        np.testing.assert_allclose(o["cb_dsig"][sl], sg.grad.numpy(), rtol=2e-3, atol=2e-4 * scale)
+        np.testing.assert_allclose(o["cb_drgbs"][sl], cl.grad.numpy(), rtol=1e-4, atol=1e-6)
+        checked += 1
+    assert checked > 5
+
+
+def test_distortion_matches_quadratic_definition_and_autograd():
+    sc = scenes.scene("lego", 64, seed=8)
+    o = vc.run_oracle(sc)
+    ra, ts, dl, ws = o["rays_a"], o["ts"], o["deltas"], o["cf_ws"]
+    gL = vc.grads(64, ts.shape[0])[4]
+    checked = 0
+    for r, s, n in ra:
+        if n == 0:
+            assert o["dl_loss"][r] == 0
+            continue
+        sl = slice(s, s + n)
+        w = torch.tensor(ws[sl], dtype=torch.float64, requires_grad=True)
+        t = torch.tensor(ts[sl], dtype=torch.float64); d = torch.tensor(dl[sl], dtype=torch.float64)
+        loss = (w[:, None] * w[None, :] * (t[:, None] - t[None, :]).abs()).sum() + (w * w * d).sum() / 3   # Mip-NeRF 360 eq. 15
+        np.testing.assert_allclose(o["dl_loss"][r], loss.item(), rtol=1e-3, atol=1e-6)
+        (loss * float(gL[r])).backward()
+        sc_ = np.abs(w.grad.numpy()).max() + 1e-9
+        np.testing.assert_allclose(o["dl_dws"][sl], w.grad.numpy(), rtol=1e-3, atol=2e-3 * sc_)
+        checked += 1
+    assert checked > 10
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "vren_ref_*.npz"))) or [None])
+def test_oracle_pinned_to_reference_kernels(path):
+    """THE PIN: the CPU restatement reproduces what the reference's own CUDA kernels produced on a B200."""
+    if path is None:
+        pytest.skip("no golden vectors committed yet (run tests/golden/make_golden_vren.py on the GPU box)")
+    g = dict(np.load(path))
+    if "rays_o" not in g:   # integer utilities
+        assert np.array_equal(orc.morton3D(g["coords"]), g["morton"])
+        assert np.array_equal(orc.morton3D_invert(g["morton"]), g["inv"])
+        bf = np.zeros_like(g["bitfield"]); orc.packbits(g["grid"], float(g["thr"]), bf)
+        assert np.array_equal(bf, g["bitfield"])
+        return
+    sc = {k: g[k] for k in ("rays_o", "rays_d", "bitfield", "noise", "center", "half")}
+    sc.update(cascades=int(g["cascades"]), grid_size=int(g["grid_size"]), max_samples=int(g["max_samples"]), scale=float(g["scale"]), esf=float(g["esf"]))
+    mine = vc.run_oracle(sc)
+    problems = vc.compare(mine, g, exact_expf=False, label=os.path.basename(path) + ": ")
+    assert not problems, "\n".join(problems)
