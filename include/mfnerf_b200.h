@@ -26,6 +26,11 @@ extern "C" {
 #define MFN_DTYPE_F16 1
 #define MFN_DTYPE_F64 2
 
+/* output activations of the MLP ops */
+#define MFN_ACT_NONE 0
+#define MFN_ACT_SIGMOID 1
+#define MFN_ACT_EXP 2
+
 int mfn_version(void);
 const char* mfn_last_error(void);
 /* compute capability of the current device as major*10+minor (100 on B200), -1 without a device */
@@ -98,6 +103,40 @@ int mfn_distortion_loss_fw(const float* ws, const float* deltas, const float* ts
 int mfn_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan, const float* wts_inclusive_scan, const float* ws,
                            const float* deltas, const float* ts, const int64_t* rays_a, int64_t n_rays, int64_t n_samples,
                            float* dL_dws, void* stream);
+
+/* ---- field: encodings (replace tcnn's HashGrid / SphericalHarmonics encodings, networks.py:36-47,60-67) ------- */
+#define MFN_GRID_HASH 0
+typedef struct mfn_grid_cfg {
+    int32_t n_levels;            /* L */
+    int32_t n_features;          /* F: 1, 2, 4 or 8 */
+    int32_t log2_hashmap_size;   /* T */
+    int32_t base_resolution;     /* N_min */
+    double per_level_scale;      /* b */
+    int32_t grid_type;           /* MFN_GRID_* */
+    int32_t n_tables;            /* the MF-NeRF fork's knob; 1 for the plain hash grid */
+} mfn_grid_cfg;
+/* HOST helper: level table.  offsets_host[L+1] (entries), resolutions_host[L], scales_host[L] may be NULL.
+ * Returns the total number of table entries (parameters = entries * F), <0 on error. */
+int64_t mfn_grid_layout(const mfn_grid_cfg* cfg_host, uint32_t* offsets_host, uint32_t* resolutions_host, float* scales_host);
+/* x01 (n,3) f32 in [0,1]; table fp16 (entries*F); out (n, L*F) fp16, feature order [level][feature] */
+int mfn_grid_encode_fwd(const float* x01, const void* table, const mfn_grid_cfg* cfg_host, int64_t n, void* out, void* stream);
+/* dL_dout (n, L*F) fp16; dgrid fp32 (entries*F), ACCUMULATED into with atomics (caller zeroes it) */
+int mfn_grid_encode_bwd(const float* x01, const void* dL_dout, const mfn_grid_cfg* cfg_host, int64_t n, float* dgrid, void* stream);
+/* degree-4 spherical harmonics of 2*d01-1: (n,3) f32 -> 16 fp16 values written at out[i*out_stride + out_offset ...] */
+int mfn_sh4_fwd(const float* dirs01, int64_t n, void* out, int out_stride, int out_offset, void* stream);
+
+/* ---- field: fully fused MLPs (replaces tcnn.Network / the MLP half of tcnn.NetworkWithInputEncoding,
+ * networks.py:36-57,69-79).  fp16 activations (n,in_dim) -> (n,16) (output padded to 16 like tcnn), fp16 weights laid out
+ * first->last as row-major (out x in) matrices: [width x in_dim][(n_hidden-1) x width x width][16 x width], no biases,
+ * ReLU hidden activations, `out_act` = MFN_ACT_*.  `acts` (n_hidden, n, width) fp16 receives the hidden activations
+ * when non-NULL (needed by mfn_mlp_bwd).  in_dim in {16,32,64}, width in {64,128}, n_hidden in {1,2}. */
+int64_t mfn_mlp_param_count(int in_dim, int width, int n_hidden);
+int mfn_mlp_fwd(const void* in, const void* weights, int in_dim, int width, int n_hidden, int out_act, int64_t n, void* out,
+                void* acts, void* stream);
+/* dL_dout (n,16) fp16 (already multiplied by the caller's loss scale); dL_din (n,in_dim) fp16 or NULL; dW fp32, same layout as
+ * `weights`, ACCUMULATED into (caller zeroes it). */
+int mfn_mlp_bwd(const void* dL_dout, const void* in, const void* acts, const void* out, const void* weights, int in_dim, int width,
+                int n_hidden, int out_act, int64_t n, void* dL_din, float* dW, void* stream);
 
 #ifdef __cplusplus
 }

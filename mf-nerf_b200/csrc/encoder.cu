@@ -1,0 +1,264 @@
+// Multiresolution hash-grid encoding, forward and backward, and the degree-4 spherical-harmonics encoding.
+// Replaces the tiny-cuda-nn "HashGrid" / "SphericalHarmonics" encodings the reference instantiates in
+// models/networks.py:36-47,60-67.  tcnn's source is not part of the reference tree (parity unpinned);
+// the arithmetic below follows tcnn's published algorithm as restated in SURVEY.md section 8c:
+//   per level l: scale_l = 2^(l*log2(b)) * N_min - 1, res_l = ceil(scale_l) + 1,
+//                entries_l = min(round_up(res_l^3, 8), 2^T), levels concatenated;
+//   pos = x*scale_l + 0.5, cell = floor(pos), w = pos - cell, 8 corners weighted by prod(bit ? w : 1-w);
+//   index = x + y*res + z*res^2 when res^3 <= entries_l, else (x*1 ^ y*2654435761 ^ z*805459861), both mod entries_l;
+//   features fp16, interpolation in fp32, one rounding to fp16 on output; output order [level][feature].
+// Forward: one thread per sample walks all levels (128 independent 4-byte gathers in flight per thread for L=16,F=2),
+// writes its 2*L*F output bytes with 16-byte stores.  Backward: grid.y = level (concurrent CTAs hit the same level's
+// table -> L2 locality), fp32 vector atomics (red.global.add.v2.f32 on sm_100) into a dense fp32 gradient table.
+// Algorithmic bytes/sample (L=16,F=2): fwd 12 + 512 gathered + 64 written; bwd 12 + 64 + 512 scattered.
+#include "common.cuh"
+#include "../../include/mfnerf_b200.h"
+#include <math.h>
+
+namespace mfn {
+
+constexpr int kMaxLevels = 32;
+
+struct GridMeta {
+    uint32_t offset[kMaxLevels + 1];  // in entries
+    uint32_t res[kMaxLevels];
+    float scale[kMaxLevels];
+    uint32_t hashed;                  // bit l set: level l is hashed
+    int n_levels;
+};
+
+static int build_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
+    if (!cfg || cfg->n_levels < 1 || cfg->n_levels > kMaxLevels || cfg->log2_hashmap_size < 1 || cfg->log2_hashmap_size > 30 ||
+        cfg->base_resolution < 1 || !(cfg->per_level_scale > 0)) { set_error("%s: bad grid config", who); return MFN_ERR_ARG; }
+    if (cfg->n_features != 1 && cfg->n_features != 2 && cfg->n_features != 4 && cfg->n_features != 8) {
+        set_error("%s: n_features_per_level must be 1, 2, 4 or 8", who); return MFN_ERR_ARG;
+    }
+    if (cfg->grid_type != MFN_GRID_HASH) { set_error("%s: unsupported grid_type %d", who, cfg->grid_type); return MFN_ERR_ARG; }
+    // tcnn keeps per_level_scale as a float; the level scale is evaluated in double from that float and rounded to
+    // float once, which makes res_l robust against last-bit noise when scale_l is (nearly) an integer.
+    const double log2b = log2((double)(float)cfg->per_level_scale);
+    uint64_t off = 0;
+    m->hashed = 0; m->n_levels = cfg->n_levels;
+    for (int l = 0; l < cfg->n_levels; ++l) {
+        const float s = (float)(exp2((double)l * log2b) * (double)cfg->base_resolution - 1.0);
+        const uint32_t res = (uint32_t)ceilf(s) + 1u;
+        uint64_t cells = (uint64_t)res * res * res;
+        const uint64_t cap = 0x7fffffffu;
+        uint64_t entries = cells > cap ? cap : cells;
+        entries = (entries + 7) / 8 * 8;
+        const uint64_t T = 1ull << cfg->log2_hashmap_size;
+        if (entries > T) entries = T;
+        if (cells > entries) m->hashed |= 1u << l;
+        m->offset[l] = (uint32_t)off; m->res[l] = res; m->scale[l] = s;
+        off += entries;
+        if (off > 0xffffffffull) { set_error("%s: grid too large", who); return MFN_ERR_ARG; }
+    }
+    m->offset[cfg->n_levels] = (uint32_t)off;
+    return MFN_OK;
+}
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size, bool hashed) {
+    uint32_t idx;
+    if (hashed) idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
+    else idx = x + y * res + z * res * res;
+    return idx % size;
+}
+
+template <int F> struct FeatVec;
+template <> struct FeatVec<1> { using T = unsigned short; };
+template <> struct FeatVec<2> { using T = uint32_t; };
+template <> struct FeatVec<4> { using T = uint2; };
+template <> struct FeatVec<8> { using T = uint4; };
+
+template <int F>
+__device__ __forceinline__ void add_weighted(float (&acc)[F], const typename FeatVec<F>::T& raw, float w) {
+    const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = fmaf(w, __half2float(h[f]), acc[f]);
+}
+
+// interpolate one level for one sample
+template <int F>
+__device__ __forceinline__ void encode_level(const __half* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, float (&acc)[F]) {
+    const float s = m.scale[l];
+    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const bool hashed = (m.hashed >> l) & 1u;
+    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const typename FeatVec<F>::T* lvl = reinterpret_cast<const typename FeatVec<F>::T*>(table) + m.offset[l];
+    typename FeatVec<F>::T v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        v[c] = __ldg(lvl + grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed));
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * (((c >> 1) & 1) ? wy : 1.f - wy) * ((c >> 2) ? wz : 1.f - wz);
+        add_weighted<F>(acc, v[c], w);
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(128)
+grid_encode_fwd_kernel(const float* __restrict__ x01, const __half* __restrict__ table, const __grid_constant__ GridMeta m, int64_t n,
+                       __half* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    constexpr int G = 8 / F;  // levels per 16-byte store
+    __half* o = out + (size_t)i * m.n_levels * F;
+    int l = 0;
+    for (; l + G <= m.n_levels; l += G) {
+        __align__(16) __half pack[8];
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            float acc[F];
+            encode_level<F>(table, m, l + j, x, y, z, acc);
+#pragma unroll
+            for (int f = 0; f < F; ++f) pack[j * F + f] = __float2half_rn(acc[f]);
+        }
+        if (((m.n_levels * F) % 8) == 0) *reinterpret_cast<uint4*>(o + l * F) = *reinterpret_cast<const uint4*>(pack);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[l * F + k] = pack[k];
+        }
+    }
+    for (; l < m.n_levels; ++l) {
+        float acc[F];
+        encode_level<F>(table, m, l, x, y, z, acc);
+#pragma unroll
+        for (int f = 0; f < F; ++f) o[l * F + f] = __float2half_rn(acc[f]);
+    }
+}
+
+template <int F>
+__device__ __forceinline__ void atomic_add_vec(float* p, const float (&v)[F]) {
+    if constexpr (F == 2) atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+    else if constexpr (F == 4) atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) atomicAdd(p + f, v[f]);
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+grid_encode_bwd_kernel(const float* __restrict__ x01, const __half* __restrict__ dL_dout, const __grid_constant__ GridMeta m, int64_t n,
+                       float* __restrict__ dgrid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = blockIdx.y;
+    float g[F];
+    bool any = false;
+#pragma unroll
+    for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); any |= (g[f] != 0.f); }
+    if (!any) return;
+    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    const float s = m.scale[l];
+    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const bool hashed = (m.hashed >> l) & 1u;
+    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    float* lvl = dgrid + (size_t)m.offset[l] * F;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float w = ((c & 1) ? wx : 1.f - wx) * (((c >> 1) & 1) ? wy : 1.f - wy) * ((c >> 2) ? wz : 1.f - wz);
+        const uint32_t idx = grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed);
+        float v[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) v[f] = w * g[f];
+        atomic_add_vec<F>(lvl + (size_t)idx * F, v);
+    }
+}
+
+// degree-4 real spherical harmonics of v = 2*d01 - 1 (16 outputs)
+__device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void sh4_fwd_kernel(const float* __restrict__ d01, int64_t n, __half* __restrict__ out, int out_stride, int out_offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[16];
+    sh4(fmaf(d01[3 * i], 2.f, -1.f), fmaf(d01[3 * i + 1], 2.f, -1.f), fmaf(d01[3 * i + 2], 2.f, -1.f), o);
+    __align__(16) __half h[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) h[k] = __float2half_rn(o[k]);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * out_stride + out_offset);
+    dst[0] = reinterpret_cast<const uint4*>(h)[0];
+    dst[1] = reinterpret_cast<const uint4*>(h)[1];
+}
+
+}  // namespace mfn
+
+using namespace mfn;
+
+extern "C" int64_t mfn_grid_layout(const mfn_grid_cfg* cfg, uint32_t* offsets_host, uint32_t* resolutions_host, float* scales_host) {
+    GridMeta m;
+    if (build_meta(cfg, &m, "mfn_grid_layout") != MFN_OK) return -1;
+    for (int l = 0; l < cfg->n_levels; ++l) {
+        if (offsets_host) offsets_host[l] = m.offset[l];
+        if (resolutions_host) resolutions_host[l] = m.res[l];
+        if (scales_host) scales_host[l] = m.scale[l];
+    }
+    if (offsets_host) offsets_host[cfg->n_levels] = m.offset[cfg->n_levels];
+    return (int64_t)m.offset[cfg->n_levels];
+}
+
+#define MFN_F_DISPATCH(F_, BODY) \
+    switch (F_) { case 1: { constexpr int F = 1; BODY } break; case 2: { constexpr int F = 2; BODY } break; \
+                  case 4: { constexpr int F = 4; BODY } break; default: { constexpr int F = 8; BODY } break; }
+
+extern "C" int mfn_grid_encode_fwd(const float* x01, const void* table, const mfn_grid_cfg* cfg, int64_t n, void* out, void* stream) {
+    GridMeta m;
+    int rc = build_meta(cfg, &m, "mfn_grid_encode_fwd");
+    if (rc != MFN_OK) return rc;
+    if (n < 0) { set_error("mfn_grid_encode_fwd: bad n"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!x01 || !table || !out) { set_error("mfn_grid_encode_fwd: null pointer"); return MFN_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    MFN_F_DISPATCH(cfg->n_features, (grid_encode_fwd_kernel<F><<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(x01, (const __half*)table, m, n, (__half*)out));)
+    return check_launch("mfn_grid_encode_fwd", st);
+}
+
+extern "C" int mfn_grid_encode_bwd(const float* x01, const void* dL_dout, const mfn_grid_cfg* cfg, int64_t n, float* dgrid, void* stream) {
+    GridMeta m;
+    int rc = build_meta(cfg, &m, "mfn_grid_encode_bwd");
+    if (rc != MFN_OK) return rc;
+    if (n < 0) { set_error("mfn_grid_encode_bwd: bad n"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!x01 || !dL_dout || !dgrid) { set_error("mfn_grid_encode_bwd: null pointer"); return MFN_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)cfg->n_levels);
+    MFN_F_DISPATCH(cfg->n_features, (grid_encode_bwd_kernel<F><<<grid, 256, 0, st>>>(x01, (const __half*)dL_dout, m, n, dgrid));)
+    return check_launch("mfn_grid_encode_bwd", st);
+}
+
+extern "C" int mfn_sh4_fwd(const float* dirs01, int64_t n, void* out, int out_stride, int out_offset, void* stream) {
+    if (n < 0 || out_stride < 16 || out_offset < 0 || (out_stride % 8) || (out_offset % 8)) { set_error("mfn_sh4_fwd: bad argument"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!dirs01 || !out) { set_error("mfn_sh4_fwd: null pointer"); return MFN_ERR_ARG; }
+    sh4_fwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs01, n, (__half*)out, out_stride, out_offset);
+    return check_launch("mfn_sh4_fwd", (cudaStream_t)stream);
+}

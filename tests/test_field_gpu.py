@@ -1,0 +1,143 @@
+"""GPU parity tests of the field kernels (hash-grid encoder, SH, fused MLPs) against the torch
+restatement in oracle/field_ref.py.  Tolerances (tcnn parity is unpinned, see oracle/field_ref.py):
+  encoder features  : fp16 output, fp32 interpolation  -> |err| <= 1e-3 * max|feature| + 1 fp16 ulp
+  encoder gradients : fp32 atomics                      -> rtol 2e-3 on entries above 1e-3 * max
+  MLP outputs       : fp16 activations, fp32 accumulate -> rtol 2e-2 / atol 2e-3
+  MLP gradients     : dZ rounded to fp16 per layer      -> rtol 5e-2 on entries above 2e-2 * max
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import field_ref as fr
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_case(scale, T, F=2, L=16):
+    from mfnerf_b200 import field_ops as ops
+    b = float(np.exp(np.log(2048 * scale / 16) / (L - 1)))
+    cfg = ops.make_grid_cfg(L, F, T, 16, b)
+    levels, entries = fr.grid_layout(L, F, T, 16, b)
+    assert ops.grid_layout(cfg)[0] == entries
+    return cfg, levels, entries
+
+
+@pytest.mark.parametrize("scale,T,F,L", [(0.5, 19, 2, 16), (16.0, 21, 2, 16), (0.5, 15, 4, 8), (0.5, 14, 1, 16), (4.0, 16, 8, 4)])
+def test_grid_encode_forward_backward(scale, T, F, L):
+    from mfnerf_b200 import field_ops as ops
+    cfg, levels, entries = _grid_case(scale, T, F, L)
+    g = torch.Generator().manual_seed(0)
+    N = 4099
+    x = torch.rand(N, 3, generator=g)
+    x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [1, 0, 0.5], [0.5, 0.5, 0.5], [0.999999, 1e-7, 0.25], [0, 1, 0], [0.3333, 0.6667, 1], [1, 1, 0]])
+    table = (torch.rand(entries * F, generator=g) * 2 - 1).half()
+    xd, td = x.cuda(), table.cuda()
+    out = ops.grid_encode_fwd(xd, td, cfg)
+    tab32 = table.float().cuda().requires_grad_(True)
+    want = fr.grid_encode(xd, tab32, levels, F)
+    err = (out.float() - want).abs().max().item()
+    assert err <= 1e-3 * want.abs().max().item() + 1e-3, err
+    # backward: dL/dtable for a random fp16 upstream gradient
+    dy = (torch.randn(N, L * F, generator=g) * 0.1).half().cuda()
+    dgrid = torch.zeros(entries * F, device="cuda")
+    ops.grid_encode_bwd(xd, dy, cfg, dgrid)
+    (want * dy.float()).sum().backward()
+    ref = tab32.grad
+    big = ref.abs() > 1e-3 * ref.abs().max()
+    assert big.sum() > 100
+    torch.testing.assert_close(dgrid[big], ref[big], rtol=2e-3, atol=1e-5)
+    assert (dgrid[~big] - ref[~big]).abs().max() <= 2e-3 * ref.abs().max()
+    assert (dgrid == 0).sum() == (ref == 0).sum()   # exactly the touched rows receive gradient
+
+
+def test_sh4():
+    from mfnerf_b200 import field_ops as ops
+    d = torch.randn(5000, 3, generator=torch.Generator().manual_seed(1))
+    d = d / d.norm(dim=1, keepdim=True)
+    d01 = ((d + 1) / 2).cuda()
+    out = ops.sh4_fwd(d01)
+    want = fr.sh4(d01)
+    torch.testing.assert_close(out.float(), want, rtol=2e-3, atol=1e-3)
+    # written in place into a wider row (the [SH | h] concat of networks.py:147)
+    buf = torch.zeros(5000, 32, dtype=torch.float16, device="cuda")
+    ops.sh4_fwd(d01, out=buf, out_offset=0)
+    assert torch.equal(buf[:, :16], out) and (buf[:, 16:] == 0).all()
+
+
+@pytest.mark.parametrize("in_dim,width,n_hidden,act,N", [(32, 64, 1, "None", 1000), (32, 64, 2, "Sigmoid", 4099), (32, 128, 2, "Sigmoid", 777),
+                                                        (16, 64, 1, "Sigmoid", 129), (64, 64, 2, "None", 1), (32, 64, 2, "Sigmoid", 128 * 300 + 5)])
+def test_mlp_forward_backward(in_dim, width, n_hidden, act, N):
+    from mfnerf_b200 import field_ops as ops
+    g = torch.Generator().manual_seed(2)
+    n_w = ops.mlp_param_count(in_dim, width, n_hidden)
+    assert n_w == width * in_dim + (n_hidden - 1) * width * width + 16 * width
+    w = ((torch.rand(n_w, generator=g) * 2 - 1) * (6 / (in_dim + width)) ** 0.5).half()
+    x = torch.randn(N, in_dim, generator=g).half()
+    xd, wd = x.cuda(), w.cuda()
+    out, acts = ops.mlp_fwd(xd, wd, in_dim, width, n_hidden, act)
+    w32 = w.float().cuda().requires_grad_(True); x32 = x.float().cuda().requires_grad_(True)
+    want, hidden = fr.mlp(x32, w32, in_dim, width, n_hidden, act, return_hidden=True)
+    torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-3)
+    for l in range(n_hidden):
+        torch.testing.assert_close(acts[l].float(), hidden[l], rtol=2e-2, atol=2e-3)
+    dy = (torch.randn(N, 16, generator=g) * 0.05).half().cuda()
+    dW = torch.zeros(n_w, device="cuda")
+    dx = ops.mlp_bwd(dy, xd, acts, out, wd, in_dim, width, n_hidden, act, dW)
+    (want * dy.float()).sum().backward()
+    for got, ref, name in ((dx.float(), x32.grad, "dx"), (dW, w32.grad, "dW")):
+        scale = ref.abs().max().item()
+        err = (got - ref).abs()
+        big = ref.abs() > 2e-2 * scale
+        assert (err[big] <= 5e-2 * ref.abs()[big] + 1e-3 * scale).all(), (name, err.max().item(), scale)
+        assert err.max().item() <= 2e-2 * scale, (name, err.max().item(), scale)
+    # accumulate semantics: a second backward doubles dW
+    ops.mlp_bwd(dy, xd, acts, out, wd, in_dim, width, n_hidden, act, dW, need_dx=False)
+    torch.testing.assert_close(dW, 2 * w32.grad, rtol=5e-2, atol=2e-2 * w32.grad.abs().max().item())
+
+
+def test_tcnn_dropin_modules_match_ngp_restatement():
+    """the three tcnn modules wired exactly like models/networks.py:96-155, against oracle NGPRef with the same params"""
+    import tinycudann as tcnn
+    scale = 0.5
+    b = float(np.exp(np.log(2048 * scale / 16) / 15))
+    xyz_encoder = tcnn.NetworkWithInputEncoding(3, 16, {"otype": "HashGrid", "type": "Hash", "n_levels": 16, "n_features_per_level": 2,
+                                                        "log2_hashmap_size": 19, "base_resolution": 16, "n_tables": 1, "per_level_scale": b,
+                                                        "interpolation": "Linear"},
+                                                {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64,
+                                                 "n_hidden_layers": 1}).cuda()
+    dir_encoder = tcnn.Encoding(3, {"otype": "SphericalHarmonics", "degree": 4}).cuda()
+    rgb_net = tcnn.Network(32, 3, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid", "n_neurons": 64,
+                                   "n_hidden_layers": 2}).cuda()
+    assert xyz_encoder.params.shape[0] - 3072 == 2 * fr.grid_layout(16, 2, 19, 16, b)[1] and rgb_net.params.shape[0] == 7168
+    assert dir_encoder.params.shape[0] == 0 and xyz_encoder.params.dtype == torch.float32
+    with torch.no_grad():   # make the grid features matter
+        xyz_encoder.params[3072:].uniform_(-0.5, 0.5)
+    ref = fr.NGPRef(scale, params=(xyz_encoder.params.detach().cpu(), rgb_net.params.detach().cpu())).cuda()
+    g = torch.Generator().manual_seed(3)
+    N = 5000
+    x = ((torch.rand(N, 3, generator=g) - 0.5) * 2 * scale).cuda()
+    d = torch.randn(N, 3, generator=g).cuda()
+
+    def ours(x, d):
+        x01 = (x - (-scale)) / (scale - (-scale))
+        h = xyz_encoder(x01)
+        sig = torch.exp(h[:, 0].float())
+        dn = d / torch.norm(d, dim=1, keepdim=True)
+        rgbs = rgb_net(torch.cat([dir_encoder((dn + 1) / 2), h], 1))
+        return sig, rgbs
+    sig, rgbs = ours(x, d)
+    assert rgbs.dtype == torch.float16 and rgbs.shape == (N, 3)
+    sig_r, rgbs_r = ref(x, d)
+    torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=1e-3)
+    torch.testing.assert_close(rgbs.float(), rgbs_r, rtol=2e-2, atol=3e-3)
+    gs, gc = torch.randn(N, generator=g).cuda() * 1e-2, torch.randn(N, 3, generator=g).cuda() * 1e-2
+    ((sig * gs).sum() + (rgbs.float() * gc).sum()).backward()
+    ((sig_r * gs).sum() + (rgbs_r * gc).sum()).backward()
+    for got, want, name in ((xyz_encoder.params.grad, ref.xyz_params.grad, "xyz"), (rgb_net.params.grad, ref.rgb_params.grad, "rgb")):
+        sc = want.abs().max().item()
+        err = (got - want).abs()
+        big = want.abs() > 5e-2 * sc
+        assert big.sum() > 50
+        assert (err[big] <= 8e-2 * want.abs()[big] + 2e-3 * sc).all(), (name, err[big].max().item(), sc)
+        assert err.max().item() <= 3e-2 * sc, (name, err.max().item(), sc)
