@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- training rays/s (and samples/s, 800x800 render FPS) of the MF-NeRF hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels through the C ABI)
+    python bench.py --impl reference [...]                          the reference path on the host cores (port, see oracle/cpu_step.py)
+    torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU, rays sharded, NCCL all-reduce of the gradients
+
+Workload (BASELINE.json configs[1]): Lego-shaped synthetic scene, 800x800 pinhole cameras on a hemisphere of radius 1.5, 8192 rays
+per step per GPU, scale 0.5 (one cascade, dt = sqrt(3)/1024), hash grid L16 F2 T2^19, 64x1 sigma net, 64x2 rgb net, random-init weights,
+analytic box-scene colours as targets.  One "step" = the reference's training_step (train.py:164-190): [update_density_grid every 16
+steps] -> AABB -> march -> field -> composite -> loss -> backward -> [all-reduce] -> Adam.  The occupancy grid starts from the procedural
+Lego voxelisation, i.e. the post-warm-up regime, and then evolves through the real update rule.
+
+value  = rays/s over K steps with every ray batch already resident in HBM (a pool of distinct batches, cycled);
+e2e    = the same K steps fed from pinned HOST memory (H2D of rays+targets every step, D2H of the loss every step);
+roofline / breakdown = per-kernel CUDA-event times recorded inside the replayed CUDA graph in a separate pass of the same steps.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "mf-nerf_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+R_PER_GPU = 8192
+POOL = 64                      # distinct ray batches cycled through (64 x 8192 rays)
+METRIC = "train_rays_per_sec"
+UNIT = "rays/s"
+WORKLOAD = "lego_synthetic_train_8192rays_scale0.5_hashL16F2T19"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sust=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def make_pool(n_batches, rays, seed):
+    """-> float32 numpy (n_batches, 3, rays, 3): [rays_o, rays_d, target] per batch"""
+    import numpy as np
+    from mfnerf_b200 import synthetic as syn
+    o, d, _, _ = syn.random_rays(n_batches * rays, seed=seed)
+    tgt = syn.analytic_render(o, d).numpy()
+    pool = np.stack([o.reshape(n_batches, rays, 3), d.reshape(n_batches, rays, 3), tgt.reshape(n_batches, rays, 3)], 1)
+    return np.ascontiguousarray(pool, dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons with NVML while the timed region runs"""
+
+    def __init__(self, torch_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80, "sw_power_cap": 0x4}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (host cores)
+def cpu_reference(steps, warmup, rays=R_PER_GPU, budget_s=25.0):
+    """the reference training step as a CPU port (oracle/cpu_step.py) on all host cores -> (rays/s, dict)"""
+    import numpy as np
+    from mfnerf_b200 import synthetic as syn
+    from oracle.cpu_step import CpuTrainer
+    tr = CpuTrainer(scale=0.5, log2_T=19, threads=os.cpu_count())
+    tr.set_density_grid(syn.lego_density_grid(0.5, 1))
+    pool = make_pool(2, rays, seed=101)
+    for i in range(max(1, warmup)):
+        tr.train_step(pool[i % 2, 0], pool[i % 2, 1], pool[i % 2, 2])
+    t0 = time.perf_counter()
+    done = samples = 0
+    for i in range(steps):
+        _, n = tr.train_step(pool[i % 2, 0], pool[i % 2, 1], pool[i % 2, 2])
+        done += 1; samples += n
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * rays / dt, dict(steps_run=done, seconds=dt, samples_per_ray=samples / max(1, done * rays), cores=tr.threads,
+                                  sample=f"{done} full training steps of {rays} rays (AABB, march, field fwd/bwd, composite fw/bw, loss, Adam) "
+                                         f"of the same Lego-shaped workload, {dt:.1f} s of CPU work")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 20)
+    v, info = cpu_reference(steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps_run"], "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps_run"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_step": R_PER_GPU, "note": "vren/tcnn have no CPU kernels: C restatement of vren + torch "
+                   "transliteration of tcnn (oracle/), all host threads"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "samples_per_ray": info["samples_per_ray"],
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+# algorithmic bytes per sample / per ray / per parameter, or FLOPs per sample, of every profiled kernel
+def algorithmic(name, n_samples, n_rays, n_params, rgb_flops):
+    tab = {
+        "grid_encode_fwd": ("hbm", 588.0 * n_samples), "grid_encode_bwd": ("hbm", 588.0 * n_samples),
+        "march_count": ("hbm", 60.0 * n_rays + 8.0 * n_samples), "march_write": ("hbm", 24.0 * n_rays + 40.0 * n_samples),
+        "composite_train_fw": ("hbm", 28.0 * n_samples + 52.0 * n_rays), "composite_train_bw": ("hbm", 48.0 * n_samples + 64.0 * n_rays),
+        "adam": ("hbm", 30.0 * n_params),
+        "mlp_sigma_fwd": ("tensor", 6144.0 * n_samples), "mlp_rgb_fwd": ("tensor", rgb_flops * n_samples),
+        "mlp_sigma_bwd": ("tensor", 2 * 6144.0 * n_samples), "mlp_rgb_bwd": ("tensor", 2 * rgb_flops * n_samples),
+        "field_fwd": ("hbm", 588.0 * n_samples), "field_bwd": ("hbm", 588.0 * n_samples),
+    }
+    return tab.get(name)
+
+
+PROFILED = ["march_count", "march_scan", "march_write", "grid_encode_fwd", "mlp_sigma_fwd", "sh_sigma", "mlp_rgb_fwd", "field_fwd", "composite_train_fw",
+            "nerf_loss", "composite_train_bw", "prep_dout2", "mlp_rgb_bwd", "merge_dh", "mlp_sigma_bwd", "grid_encode_bwd", "field_bwd", "adam"]
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mfnerf_b200 import _lib
+    from mfnerf_b200 import synthetic as syn
+    from mfnerf_b200.engine import NGPEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the host-core port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    R = R_PER_GPU
+
+    eng = NGPEngine(scale=0.5, n_rays=R, device=dev, world_size=world, seed=1337)
+    eng.density_grid.copy_(torch.from_numpy(syn.lego_density_grid(0.5, 1)).to(dev))
+    eng.repack_bitfield(0.5)
+    pool_host = torch.from_numpy(make_pool(POOL, R, seed=1000 + rank)).pin_memory()
+    pool_dev = pool_host.to(dev)
+    loss_host = torch.zeros(K + W + 8, 3).pin_memory()
+    torch.cuda.synchronize(dev)
+
+    # steps start at 1: step 0 would be the reference's first update_density_grid from an untrained network (warm-up regime)
+    state = {"step": 1}
+
+    def step_from(pool, i_host_loss=None):
+        s = state["step"]
+        eng.train_step_packed(pool[s % POOL], global_step=s)
+        if i_host_loss is not None:
+            loss_host[i_host_loss].copy_(eng.loss_terms, non_blocking=True)
+        state["step"] = s + 1
+
+    # ---- warm-up (eager first so that lazy initialisation happens outside capture), then capture
+    for _ in range(3):
+        step_from(pool_dev)
+    if not args.no_graph:
+        eng.capture()
+    launches_per_fb = eng.launches_per_forward_backward
+    for _ in range(W):
+        step_from(pool_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(pool, with_loss_readback):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.samples_acc.zero_()
+        l0 = _lib.lib.mfn_launch_count(); g0 = eng.graph_replays
+        barrier()
+        ev0.record()
+        for i in range(K):
+            step_from(pool, i if with_loss_readback else None)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        launches = (_lib.lib.mfn_launch_count() - l0) + (eng.graph_replays - g0) * launches_per_fb
+        samples = float(eng.samples_acc.item())
+        if world > 1:
+            t = torch.tensor([samples], device=dev, dtype=torch.float64); dist.all_reduce(t); samples = float(t.item())
+        return ms, launches, samples
+
+    # ---- device-resident run (value)
+    sampler = ClockSampler(local); sampler.start()
+    ms_dev, launches, samples_dev = timed(pool_dev, False)
+    clocks = sampler.stop()
+    # ---- end-to-end run: rays + targets from pinned host memory every step, loss read back every step
+    ms_e2e, _, _ = timed(pool_host, True)
+    rays_total = float(K) * R * world
+    value = rays_total / (ms_dev * 1e-3)
+    e2e = rays_total / (ms_e2e * 1e-3)
+    final_loss = loss_host[K - 1].tolist()
+
+    # ---- per-kernel breakdown: CUDA events recorded inside the (re-captured) graph, one synchronised replay per step
+    breakdown, roofline = {}, None
+    pk = peaks()
+    if rank == 0:
+        evs = {}
+        for name in PROFILED:
+            a, b = _lib.lib.mfn_event_create(), _lib.lib.mfn_event_create()
+            evs[name] = (a, b)
+            _lib.check(_lib.lib.mfn_profile_set(name.encode(), a, b), "mfn_profile_set")
+    if rank == 0 and not args.no_graph:
+        eng.capture()
+    n_prof = min(K, 48)
+    acc = {n: [] for n in PROFILED}
+    smp = []
+    for i in range(n_prof):
+        step_from(pool_dev)
+        if rank == 0:
+            torch.cuda.synchronize(dev)
+            smp.append(int(eng.counter[0].item()))
+            ms = ctypes.c_float()
+            for name, (a, b) in evs.items():
+                if _lib.lib.mfn_event_elapsed_ms(a, b, ctypes.byref(ms)) == 0:
+                    acc[name].append(ms.value)
+    if rank == 0:
+        _lib.lib.mfn_profile_set(b"", None, None)
+        if not args.no_graph:
+            eng.capture()
+        mean_s = float(np.mean(smp)) if smp else 0.0
+        rgb_flops = 2.0 * (32 * 64 + 64 * 64 + 64 * 3)
+        for name in PROFILED:
+            if acc[name]:
+                breakdown[name] = round(float(np.mean(acc[name][2:] or acc[name])) * 1e3, 2)     # microseconds
+        if breakdown:
+            top = max(breakdown, key=breakdown.get)
+            alg = algorithmic(top, mean_s, R, eng.n_params, rgb_flops)
+            if alg:
+                bound, work = alg
+                dur = breakdown[top] * 1e-6
+                if bound == "hbm":
+                    ach, peak, unit = work / dur / 1e9, pk["hbm"], "GB/s"
+                else:
+                    ach, peak, unit = work / dur / 1e12, pk["tf_sust"], "TFLOP/s"
+                traffic = None
+                try:
+                    tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+                    if top in tj:
+                        traffic = tj[top]["dram_bytes_per_sample"] * mean_s
+                except Exception:
+                    pass
+                roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
+                            "peak_source": pk["src"], "launch_us": breakdown[top], "algorithmic_per_launch": work, "samples_per_launch": mean_s}
+
+    # ---- 800x800 test-time render (second half of the metric), on the trained state
+    render = None
+    if rank == 0 and not args.no_render:
+        pose = syn.camera_poses(4, seed=7)
+        frames = []
+        for k in range(4):
+            o, d = syn.image_rays(pose[k])
+            o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = eng.render(o, d); e1.record(); torch.cuda.synchronize(dev)
+            frames.append(e0.elapsed_time(e1))
+        ms_frame = float(np.mean(frames[1:]))
+        render = {"fps_800x800": 1e3 / ms_frame, "ms_per_frame": ms_frame, "samples_per_ray": float(out["total_samples"]) / (800 * 800)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, info = cpu_reference(12, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of fp32 grads" if world > 1 else ""),
+                       "density_grid_update_every": 16, "optimizer": "fused Adam eps=1e-15 inside the timed region", "cuda_graph": not args.no_graph,
+                       "l2": "per-step working set (fp32 params+grads+Adam moments 183 MB, fp16 table 23 MB, sample arrays) exceeds the 126 MB L2; "
+                             f"{POOL} distinct ray batches are cycled",
+                       "mixed_precision": "fp16 table/weights/activations, fp32 accumulation, fp32 master params (reference: AMP precision=16)"},
+            "samples_per_sec": samples_dev / (ms_dev * 1e-3), "samples_per_ray": samples_dev / rays_total,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(3 * R * 3 * 4), "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K,
+                    "api": "NGPEngine.train_step_packed(host_pinned_batch) -> C ABI; loss copied to pinned host memory every step"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "render": render,
+            "final_loss_terms": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,17 @@ const char* mfn_last_error(void);
 /* compute capability of the current device as major*10+minor (100 on B200), -1 without a device */
 int mfn_device_arch(void);
 
+/* ---- measurement hooks (bench.py): kernel launches issued so far by this library, and CUDA-event bracketing of named
+ * kernels (names: march_count, march_write, grid_encode_fwd, grid_encode_bwd, mlp_sigma_fwd, mlp_rgb_fwd, mlp_sigma_bwd,
+ * mlp_rgb_bwd, mlp_fwd, mlp_bwd, composite_train_fw, composite_train_bw, adam, ...).  mfn_profile_set registers one
+ * (name, start, stop) entry per call (up to 32; an empty name clears the table).  The events are recorded on the launch stream
+ * and also work inside stream capture, so a kernel can be timed inside a replayed CUDA graph. */
+int64_t mfn_launch_count(void);
+void* mfn_event_create(void);
+int mfn_event_destroy(void* event);
+int mfn_event_elapsed_ms(void* start_event, void* stop_event, float* ms_host);
+int mfn_profile_set(const char* kernel_name, void* start_event, void* stop_event);
+
 /* ---- grid utilities -------------------------------------------------------------------------------- */
 /* replaces vren.morton3D  (binding.cpp:47-51 -> raymarching.cu:62-87): coords (n,3) int32 -> indices (n) int32 */
 int mfn_morton3d(const int32_t* coords, int64_t n, int32_t* indices, void* stream);
@@ -44,6 +55,11 @@ int mfn_morton3d_invert(const int32_t* indices, int64_t n, int32_t* coords, void
 /* replaces vren.packbits (binding.cpp:35-44 -> raymarching.cu:122-161): bit i of byte k = grid[8k+i] > thr.
  * grid holds 8*n_bytes elements of `dtype` (MFN_DTYPE_*). */
 int mfn_packbits(const void* density_grid, int dtype, int64_t n_bytes, float density_threshold, uint8_t* density_bitfield, void* stream);
+
+/* same, fp32 grid, threshold = min(*threshold_dev, max_threshold) read on the device: lets update_density_grid
+ * (networks.py:268-271: packbits(grid, min(mean_density, density_threshold))) run without the .item() host sync */
+int mfn_packbits_dev_thr(const float* density_grid, int64_t n_bytes, float max_threshold, const float* threshold_dev,
+                         uint8_t* density_bitfield, void* stream);
 
 /* ---- intersection ---------------------------------------------------------------------------------- */
 /* replaces vren.ray_aabb_intersect (binding.cpp:4-16 -> intersection.cu:59-100).
@@ -137,6 +153,51 @@ int mfn_mlp_fwd(const void* in, const void* weights, int in_dim, int width, int 
  * `weights`, ACCUMULATED into (caller zeroes it). */
 int mfn_mlp_bwd(const void* dL_dout, const void* in, const void* acts, const void* out, const void* weights, int in_dim, int width,
                 int n_hidden, int out_act, int64_t n, void* dL_din, float* dW, void* stream);
+
+/* ---- field: the whole NGP field as one op pair (replaces NGP.density / NGP.forward, networks.py:96-155, and
+ * TruncExp, custom_functions.py:162-173).  xyz_params_h = fp16 copy of `xyz_encoder.params` ([3072 MLP | grid]),
+ * rgb_params_h = fp16 copy of `rgb_net.params`.  The sample count is min(*n_dev, n_max) when n_dev != NULL (device
+ * memory), else n_max: no host synchronisation is needed between the marcher and the field. */
+typedef struct mfn_field_cfg {
+    mfn_grid_cfg grid;
+    int32_t sigma_width, sigma_hidden;   /* 64, 1 (networks.py:48-57) */
+    int32_t rgb_width, rgb_hidden;       /* hparams.rgb_channels, hparams.rgb_layers */
+    int32_t rgb_act;                     /* MFN_ACT_SIGMOID, or MFN_ACT_NONE with --use_exposure */
+    float xyz_min[3], xyz_max[3];        /* scene box: x01 = (x - xyz_min) / (xyz_max - xyz_min) */
+} mfn_field_cfg;
+int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg_host, int64_t n_max, int training);
+/* xyzs, dirs (n,3) f32 -> sigmas (n) f32, rgbs (n,3) f32 (values rounded to fp16 like tcnn's output) */
+int mfn_field_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, const float* dirs,
+                  int64_t n_max, const int32_t* n_dev, float* sigmas, float* rgbs, void* workspace, int64_t workspace_bytes, void* stream);
+/* needs the workspace of the matching mfn_field_fwd call (training=1 size).  d_*_params: fp32, same layout as the
+ * parameters, ACCUMULATED into and left multiplied by loss_scale; *overflow_flag is set to 1 if an fp16 gradient overflowed. */
+int mfn_field_bwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
+                  const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale, float* d_xyz_params,
+                  float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+/* density only (NGP.density, used by update_density_grid, networks.py:258) */
+int mfn_density_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
+                    float* sigmas, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- per-ray loss (losses.py:47-60 NeRFLoss + train.py:178 + background blend rendering.py:153-161) --------------- */
+/* loss = mean((rgb + bg*(1-opacity) - target)^2) + mean(lambda_o * -(o+1e-10)*log(o+1e-10)) [+ mean(lambda_d * distortion)].
+ * Writes the gradients w.r.t. rgb (n,3), opacity (n) and, if distortion != NULL, the per-ray distortion loss (n), each
+ * multiplied by grad_scale; loss_out (3 floats, device, ACCUMULATED) receives the three terms; rgb_final may be NULL.
+ * bg_rgb_host: 3 floats in HOST memory. */
+int mfn_nerf_loss_fwbw(const float* rgb, const float* opacity, const float* target, const float* distortion, int64_t n_rays,
+                       const float* bg_rgb_host, float lambda_opacity, float lambda_distortion, float grad_scale, float* dL_drgb,
+                       float* dL_dopacity, float* dL_ddistortion, float* rgb_final, float* loss_out, void* stream);
+/* replaces torch_scatter.segment_csr(src, indptr) (sum) in RayMarcher.backward (custom_functions.py:102-112):
+ * src (rows, width) f32, indptr (n_segments+1) int64 -> out (n_segments, width) f32 */
+int mfn_segment_sum(const float* src, const int64_t* indptr, int64_t n_segments, int width, float* out, void* stream);
+/* rendering.py:29: hits_t (n,2), t1 in [0, near) -> near */
+int mfn_clamp_near(float* hits_t, int64_t n_rays, float near_distance, void* stream);
+
+/* ---- optimiser (train.py:136 FusedAdam(eps=1e-15)) ---------------------------------------- */
+/* p -= lr * mhat / (sqrt(vhat) + eps) with g = grads * grad_scale; skipped when *skip_flag != 0; params_h (fp16 shadow,
+ * may be NULL) refreshed; grads zeroed afterwards when zero_grad != 0.  `step` is 1-based. */
+int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
+int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

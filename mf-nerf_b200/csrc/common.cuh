@@ -15,7 +15,15 @@
 namespace mfn {
 
 void set_error(const char* fmt, ...);
-int check_launch(const char* what, cudaStream_t stream);
+int check_launch(const char* what, cudaStream_t stream);   // also counts one kernel launch
+void note_launch(int k);                                    // extra launches of a multi-kernel entry point
+// Brackets a kernel launch with the CUDA events registered through mfn_profile_set() when `name` matches; works
+// inside stream capture (event-record nodes), so a kernel can be timed inside a replayed CUDA graph.
+struct ProfScope {
+    cudaStream_t st; int slot;
+    ProfScope(const char* name, cudaStream_t stream);
+    ~ProfScope();
+};
 
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this

@@ -181,6 +181,7 @@ extern "C" int mfn_composite_train_fw(const float* sigmas, const float* rgbs, co
     if (n_rays < 0) { set_error("mfn_composite_train_fw: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0) return MFN_OK;
     if (!rays_a || !total_samples || !opacity || !depth || !rgb) { set_error("mfn_composite_train_fw: null pointer"); return MFN_ERR_ARG; }
+    ProfScope ps("composite_train_fw", (cudaStream_t)stream);
     composite_train_fw_kernel<<<(int)ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, T_threshold, n_rays, total_samples, opacity, depth, rgb, ws);
     return check_launch("mfn_composite_train_fw", (cudaStream_t)stream);
@@ -195,6 +196,7 @@ extern "C" int mfn_composite_train_bw(const float* dL_dopacity, const float* dL_
     if (n_rays < 0) { set_error("mfn_composite_train_bw: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0) return MFN_OK;
     if (!rays_a || !dL_dopacity || !dL_ddepth || !dL_drgb || !opacity || !depth || !rgb) { set_error("mfn_composite_train_bw: null pointer"); return MFN_ERR_ARG; }
+    ProfScope ps("composite_train_bw", (cudaStream_t)stream);
     composite_train_bw_kernel<<<(int)ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
         dL_dopacity, dL_ddepth, dL_drgb, dL_dws, sigmas, rgbs, ws, deltas, ts, rays_a, opacity, depth, rgb, T_threshold, n_rays,
         dL_dsigmas, dL_drgbs);

@@ -76,6 +76,7 @@ extern "C" int mfn_distortion_loss_fw(const float* ws, const float* deltas, cons
     if (n_rays < 0) { set_error("mfn_distortion_loss_fw: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0) return MFN_OK;
     if (!rays_a || !loss) { set_error("mfn_distortion_loss_fw: null pointer"); return MFN_ERR_ARG; }
+    ProfScope ps("distortion_fw", (cudaStream_t)stream);
     distortion_fw_kernel<<<(int)ceil_div(n_rays, kDistWarps), kDistWarps * 32, 0, (cudaStream_t)stream>>>(
         ws, deltas, ts, rays_a, n_rays, loss, ws_inclusive_scan, wts_inclusive_scan);
     return check_launch("mfn_distortion_loss_fw", (cudaStream_t)stream);
@@ -88,6 +89,7 @@ extern "C" int mfn_distortion_loss_bw(const float* dL_dloss, const float* ws_inc
     if (n_rays < 0) { set_error("mfn_distortion_loss_bw: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0) return MFN_OK;
     if (!rays_a || !dL_dloss) { set_error("mfn_distortion_loss_bw: null pointer"); return MFN_ERR_ARG; }
+    ProfScope ps("distortion_bw", (cudaStream_t)stream);
     distortion_bw_kernel<<<(int)ceil_div(n_rays, kDistWarps), kDistWarps * 32, 0, (cudaStream_t)stream>>>(
         dL_dloss, ws_inclusive_scan, wts_inclusive_scan, ws, deltas, ts, rays_a, n_rays, dL_dws);
     return check_launch("mfn_distortion_loss_bw", (cudaStream_t)stream);

@@ -11,23 +11,13 @@
 // writes its 2*L*F output bytes with 16-byte stores.  Backward: grid.y = level (concurrent CTAs hit the same level's
 // table -> L2 locality), fp32 vector atomics (red.global.add.v2.f32 on sm_100) into a dense fp32 gradient table.
 // Algorithmic bytes/sample (L=16,F=2): fwd 12 + 512 gathered + 64 written; bwd 12 + 64 + 512 scattered.
-#include "common.cuh"
-#include "../../include/mfnerf_b200.h"
+#include "field_internal.h"
+#include "sh4.cuh"
 #include <math.h>
 
 namespace mfn {
 
-constexpr int kMaxLevels = 32;
-
-struct GridMeta {
-    uint32_t offset[kMaxLevels + 1];  // in entries
-    uint32_t res[kMaxLevels];
-    float scale[kMaxLevels];
-    uint32_t hashed;                  // bit l set: level l is hashed
-    int n_levels;
-};
-
-static int build_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
+int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
     if (!cfg || cfg->n_levels < 1 || cfg->n_levels > kMaxLevels || cfg->log2_hashmap_size < 1 || cfg->log2_hashmap_size > 30 ||
         cfg->base_resolution < 1 || !(cfg->per_level_scale > 0)) { set_error("%s: bad grid config", who); return MFN_ERR_ARG; }
     if (cfg->n_features != 1 && cfg->n_features != 2 && cfg->n_features != 4 && cfg->n_features != 8) {
@@ -101,13 +91,25 @@ __device__ __forceinline__ void encode_level(const __half* __restrict__ table, c
     }
 }
 
+// sample position in [0,1]^3; with e.normalize the world position is mapped exactly like networks.py:105,
+// x = (x - xyz_min) / (xyz_max - xyz_min), in IEEE fp32
+__device__ __forceinline__ void load_pos(const EncArgs& e, int64_t i, float& x, float& y, float& z) {
+    x = e.x[3 * i]; y = e.x[3 * i + 1]; z = e.x[3 * i + 2];
+    if (e.normalize) {
+        x = __fdiv_rn(__fsub_rn(x, e.mn[0]), __fsub_rn(e.mx[0], e.mn[0]));
+        y = __fdiv_rn(__fsub_rn(y, e.mn[1]), __fsub_rn(e.mx[1], e.mn[1]));
+        z = __fdiv_rn(__fsub_rn(z, e.mn[2]), __fsub_rn(e.mx[2], e.mn[2]));
+    }
+}
+
 template <int F>
 __global__ void __launch_bounds__(128)
-grid_encode_fwd_kernel(const float* __restrict__ x01, const __half* __restrict__ table, const __grid_constant__ GridMeta m, int64_t n,
+grid_encode_fwd_kernel(const __grid_constant__ EncArgs e, const __half* __restrict__ table, const __grid_constant__ GridMeta m,
                        __half* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    const int64_t n = e.n_dev ? min((int64_t)*e.n_dev, e.n_max) : e.n_max;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x, y, z;
+    load_pos(e, i, x, y, z);
     constexpr int G = 8 / F;  // levels per 16-byte store
     __half* o = out + (size_t)i * m.n_levels * F;
     int l = 0;
@@ -132,6 +134,7 @@ grid_encode_fwd_kernel(const float* __restrict__ x01, const __half* __restrict__
 #pragma unroll
         for (int f = 0; f < F; ++f) o[l * F + f] = __float2half_rn(acc[f]);
     }
+    }
 }
 
 template <int F>
@@ -146,17 +149,19 @@ __device__ __forceinline__ void atomic_add_vec(float* p, const float (&v)[F]) {
 
 template <int F>
 __global__ void __launch_bounds__(256)
-grid_encode_bwd_kernel(const float* __restrict__ x01, const __half* __restrict__ dL_dout, const __grid_constant__ GridMeta m, int64_t n,
-                       float* __restrict__ dgrid) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restrict__ dL_dout, const __grid_constant__ GridMeta m,
+                       float* __restrict__ dgrid, int32_t* __restrict__ overflow_flag) {
+    const int64_t n = e.n_dev ? min((int64_t)*e.n_dev, e.n_max) : e.n_max;
     const int l = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float g[F];
-    bool any = false;
+    bool any = false, bad = false;
 #pragma unroll
-    for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); any |= (g[f] != 0.f); }
-    if (!any) return;
-    const float x = x01[3 * i], y = x01[3 * i + 1], z = x01[3 * i + 2];
+    for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); any |= (g[f] != 0.f); bad |= !isfinite(g[f]); }
+    if (bad && overflow_flag) *overflow_flag = 1;
+    if (!any) continue;
+    float x, y, z;
+    load_pos(e, i, x, y, z);
     const float s = m.scale[l];
     const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
     const bool hashed = (m.hashed >> l) & 1u;
@@ -174,10 +179,14 @@ grid_encode_bwd_kernel(const float* __restrict__ x01, const __half* __restrict__
         for (int f = 0; f < F; ++f) v[f] = w * g[f];
         atomic_add_vec<F>(lvl + (size_t)idx * F, v);
     }
+    }
 }
 
 // degree-4 real spherical harmonics of v = 2*d01 - 1 (16 outputs)
-__device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
+__device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {  // body shared via sh4.cuh
+    sh4_eval(x, y, z, o);
+}
+#if 0
     const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
     o[0] = 0.28209479177387814f;
     o[1] = -0.48860251190291987f * y;
@@ -196,6 +205,7 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
     o[14] = 1.4453057213202769f * z * (x2 - y2);
     o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
 }
+#endif
 
 __global__ void sh4_fwd_kernel(const float* __restrict__ d01, int64_t n, __half* __restrict__ out, int out_stride, int out_offset) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,9 +224,13 @@ __global__ void sh4_fwd_kernel(const float* __restrict__ d01, int64_t n, __half*
 
 using namespace mfn;
 
+#define MFN_F_DISPATCH(F_, BODY) \
+    switch (F_) { case 1: { constexpr int F = 1; BODY } break; case 2: { constexpr int F = 2; BODY } break; \
+                  case 4: { constexpr int F = 4; BODY } break; default: { constexpr int F = 8; BODY } break; }
+
 extern "C" int64_t mfn_grid_layout(const mfn_grid_cfg* cfg, uint32_t* offsets_host, uint32_t* resolutions_host, float* scales_host) {
     GridMeta m;
-    if (build_meta(cfg, &m, "mfn_grid_layout") != MFN_OK) return -1;
+    if (build_grid_meta(cfg, &m, "mfn_grid_layout") != MFN_OK) return -1;
     for (int l = 0; l < cfg->n_levels; ++l) {
         if (offsets_host) offsets_host[l] = m.offset[l];
         if (resolutions_host) resolutions_host[l] = m.res[l];
@@ -226,33 +240,48 @@ extern "C" int64_t mfn_grid_layout(const mfn_grid_cfg* cfg, uint32_t* offsets_ho
     return (int64_t)m.offset[cfg->n_levels];
 }
 
-#define MFN_F_DISPATCH(F_, BODY) \
-    switch (F_) { case 1: { constexpr int F = 1; BODY } break; case 2: { constexpr int F = 2; BODY } break; \
-                  case 4: { constexpr int F = 4; BODY } break; default: { constexpr int F = 8; BODY } break; }
+
+
+static inline unsigned enc_grid(int64_t n_max, int threads, int per_sm) {
+    int64_t blocks = ceil_div(n_max, threads);
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    return (unsigned)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+namespace mfn {
+int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m, int F_, __half* out, cudaStream_t st) {
+    if (e.n_max <= 0) return MFN_OK;
+    ProfScope ps("grid_encode_fwd", st);
+    MFN_F_DISPATCH(F_, (grid_encode_fwd_kernel<F><<<enc_grid(e.n_max, 128, 16), 128, 0, st>>>(e, table, m, out));)
+    return check_launch("mfn_grid_encode_fwd", st);
+}
+int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F_, float* dgrid, int32_t* overflow_flag, cudaStream_t st) {
+    if (e.n_max <= 0) return MFN_OK;
+    dim3 grid(enc_grid(e.n_max, 256, 8), (unsigned)m.n_levels);
+    ProfScope ps("grid_encode_bwd", st);
+    MFN_F_DISPATCH(F_, (grid_encode_bwd_kernel<F><<<grid, 256, 0, st>>>(e, dL_dout, m, dgrid, overflow_flag));)
+    return check_launch("mfn_grid_encode_bwd", st);
+}
+}  // namespace mfn
 
 extern "C" int mfn_grid_encode_fwd(const float* x01, const void* table, const mfn_grid_cfg* cfg, int64_t n, void* out, void* stream) {
     GridMeta m;
-    int rc = build_meta(cfg, &m, "mfn_grid_encode_fwd");
+    int rc = build_grid_meta(cfg, &m, "mfn_grid_encode_fwd");
     if (rc != MFN_OK) return rc;
     if (n < 0) { set_error("mfn_grid_encode_fwd: bad n"); return MFN_ERR_ARG; }
-    if (n == 0) return MFN_OK;
-    if (!x01 || !table || !out) { set_error("mfn_grid_encode_fwd: null pointer"); return MFN_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-    MFN_F_DISPATCH(cfg->n_features, (grid_encode_fwd_kernel<F><<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(x01, (const __half*)table, m, n, (__half*)out));)
-    return check_launch("mfn_grid_encode_fwd", st);
+    if (n > 0 && (!x01 || !table || !out)) { set_error("mfn_grid_encode_fwd: null pointer"); return MFN_ERR_ARG; }
+    EncArgs e{}; e.x = x01; e.normalize = false; e.n_max = n; e.n_dev = nullptr;
+    return grid_encode_forward(e, (const __half*)table, m, cfg->n_features, (__half*)out, (cudaStream_t)stream);
 }
 
 extern "C" int mfn_grid_encode_bwd(const float* x01, const void* dL_dout, const mfn_grid_cfg* cfg, int64_t n, float* dgrid, void* stream) {
     GridMeta m;
-    int rc = build_meta(cfg, &m, "mfn_grid_encode_bwd");
+    int rc = build_grid_meta(cfg, &m, "mfn_grid_encode_bwd");
     if (rc != MFN_OK) return rc;
     if (n < 0) { set_error("mfn_grid_encode_bwd: bad n"); return MFN_ERR_ARG; }
-    if (n == 0) return MFN_OK;
-    if (!x01 || !dL_dout || !dgrid) { set_error("mfn_grid_encode_bwd: null pointer"); return MFN_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)cfg->n_levels);
-    MFN_F_DISPATCH(cfg->n_features, (grid_encode_bwd_kernel<F><<<grid, 256, 0, st>>>(x01, (const __half*)dL_dout, m, n, dgrid));)
-    return check_launch("mfn_grid_encode_bwd", st);
+    if (n > 0 && (!x01 || !dL_dout || !dgrid)) { set_error("mfn_grid_encode_bwd: null pointer"); return MFN_ERR_ARG; }
+    EncArgs e{}; e.x = x01; e.normalize = false; e.n_max = n; e.n_dev = nullptr;
+    return grid_encode_backward(e, (const __half*)dL_dout, m, cfg->n_features, dgrid, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int mfn_sh4_fwd(const float* dirs01, int64_t n, void* out, int out_stride, int out_offset, void* stream) {

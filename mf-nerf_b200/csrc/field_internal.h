@@ -1,0 +1,50 @@
+// Internal (C++-side) launch interfaces shared by mlp.cu / encoder.cu / field.cu.  Not part of the C ABI.
+#pragma once
+#include "common.cuh"
+#include "../../include/mfnerf_b200.h"
+
+namespace mfn {
+
+constexpr int kMaxLevels = 32;
+
+struct GridMeta {
+    uint32_t offset[kMaxLevels + 1];  // in entries
+    uint32_t res[kMaxLevels];
+    float scale[kMaxLevels];
+    uint32_t hashed;                  // bit l set: level l is hashed
+    int n_levels;
+};
+int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who);
+
+// n = n_dev ? min(*n_dev, n_max) : n_max everywhere: lets a whole training step run without a host sync.
+struct MlpFwdArgs {
+    const __half* in; int in_stride;       // row stride in halfs, 0 = dense
+    const __half* W; int n_hidden; int out_act;
+    int64_t n_max; const int32_t* n_dev;
+    __half* out; int out_stride;           // 0 = 16
+    float* out_rgb32;                      // optional (n,3) fp32 copy of outputs 0..2
+    __half* acts;                          // optional (n_hidden, n_max, width)
+    const char* tag;                       // profiling name
+};
+struct MlpBwdArgs {
+    const __half* dOut;                    // (n,16) dense
+    const __half* in; int in_stride;
+    const __half* acts;
+    const __half* outv; int out_stride;
+    const __half* W; int n_hidden; int out_act;
+    int64_t n_max; const int32_t* n_dev;
+    __half* dIn; int din_stride;           // optional
+    float* dW;
+    const char* tag;
+};
+int mlp_forward(const MlpFwdArgs& a, int in_dim, int width, cudaStream_t st);
+int mlp_backward(const MlpBwdArgs& a, int in_dim, int width, cudaStream_t st);
+
+struct EncArgs {
+    const float* x; bool normalize; float mn[3], mx[3];   // normalize: x01 = (x - mn) / (mx - mn)
+    int64_t n_max; const int32_t* n_dev;
+};
+int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m, int F, __half* out, cudaStream_t st);
+int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F, float* dgrid, int32_t* overflow_flag, cudaStream_t st);
+
+}  // namespace mfn

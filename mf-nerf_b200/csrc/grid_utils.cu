@@ -34,7 +34,8 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 // bit i of byte n  =  grid[8n+i] > thr   (ref: raymarching.cu:136-138).  The reference compares in the
 // grid's own dtype for fp64; fp32/fp16 compare after promotion to float, which is what we do.
 template <typename T>
-__global__ void packbits_kernel(const T* __restrict__ grid, int64_t n_bytes, float thr, uint8_t* __restrict__ bits) {
+__global__ void packbits_kernel(const T* __restrict__ grid, int64_t n_bytes, float thr, const float* __restrict__ thr_dev, uint8_t* __restrict__ bits) {
+    if (thr_dev) thr = fminf(*thr_dev, thr);   // device-side min(mean_density, density_threshold), networks.py:270
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; n < n_bytes; n += stride) {
@@ -96,10 +97,18 @@ extern "C" int mfn_packbits(const void* grid, int dtype, int64_t n_bytes, float 
     switch (dtype) {
         case MFN_DTYPE_F32:
             if (((uintptr_t)grid & 15) != 0) { set_error("mfn_packbits: fp32 grid must be 16-byte aligned"); return MFN_ERR_ARG; }
-            packbits_kernel<float><<<g, 256, 0, st>>>((const float*)grid, n_bytes, thr, bitfield); break;
-        case MFN_DTYPE_F16: packbits_kernel<__half><<<g, 256, 0, st>>>((const __half*)grid, n_bytes, thr, bitfield); break;
+            packbits_kernel<float><<<g, 256, 0, st>>>((const float*)grid, n_bytes, thr, nullptr, bitfield); break;
+        case MFN_DTYPE_F16: packbits_kernel<__half><<<g, 256, 0, st>>>((const __half*)grid, n_bytes, thr, nullptr, bitfield); break;
         case MFN_DTYPE_F64: packbits_f64_kernel<<<g, 256, 0, st>>>((const double*)grid, n_bytes, thr, bitfield); break;
         default: set_error("mfn_packbits: unsupported dtype %d", dtype); return MFN_ERR_ARG;
     }
     return check_launch("mfn_packbits", st);
+}
+
+extern "C" int mfn_packbits_dev_thr(const float* grid, int64_t n_bytes, float max_threshold, const float* threshold_dev, uint8_t* bitfield, void* stream) {
+    if (n_bytes < 0 || (n_bytes > 0 && (!grid || !bitfield || !threshold_dev))) { set_error("mfn_packbits_dev_thr: bad argument"); return MFN_ERR_ARG; }
+    if (n_bytes == 0) return MFN_OK;
+    if (((uintptr_t)grid & 15) != 0) { set_error("mfn_packbits_dev_thr: grid must be 16-byte aligned"); return MFN_ERR_ARG; }
+    packbits_kernel<float><<<grid_for(n_bytes, 256), 256, 0, (cudaStream_t)stream>>>(grid, n_bytes, max_threshold, threshold_dev, bitfield);
+    return check_launch("mfn_packbits_dev_thr", (cudaStream_t)stream);
 }

@@ -162,9 +162,14 @@ extern "C" int mfn_march_train_count(const float* rays_o, const float* rays_d, c
     int32_t* counts = (int32_t*)workspace;
     float2* stash = (float2*)((char*)workspace + ((n_rays * 4 + 255) / 256) * 256);
     const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
-    march_count_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale,
-                                                                  exp_step_factor, noise, max_samples, n_rays, counts, stash);
-    scan_rays_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, rays_a, counter);
+    {
+        ProfScope ps("march_count", st);
+        march_count_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale,
+                                                                      exp_step_factor, noise, max_samples, n_rays, counts, stash);
+    }
+    note_launch(1);
+    { ProfScope ps("march_scan", st);
+      scan_rays_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, rays_a, counter); }
     return check_launch("mfn_march_train_count", st);
 }
 
@@ -176,6 +181,7 @@ extern "C" int mfn_march_train_write(const float* rays_o, const float* rays_d, c
     if (!rays_o || !rays_d || !rays_a || !workspace || !xyzs || !dirs || !deltas || !ts) { set_error("mfn_march_train_write: null pointer"); return MFN_ERR_ARG; }
     const float2* stash = (const float2*)((const char*)workspace + ((n_rays * 4 + 255) / 256) * 256);
     const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
+    ProfScope ps("march_write", (cudaStream_t)stream);
     march_write_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(rays_o, rays_d, rays_a, stash, max_samples, n_rays,
                                                                                     capacity, xyzs, dirs, deltas, ts);
     return check_launch("mfn_march_train_write", (cudaStream_t)stream);

@@ -8,6 +8,7 @@
 // tiles of the CTA and flushed once with fp32 atomics.
 //   FLOPs/sample: 2*(in*W + (h-1)*W*W + W*16) forward, 3x that forward+backward.
 #include "mma_utils.cuh"
+#include "field_internal.h"
 #include "../../include/mfnerf_b200.h"
 
 namespace mfn {
@@ -36,12 +37,13 @@ __device__ __forceinline__ void stage_matrix(__half* dst, int ld, const __half* 
     }
 }
 // same for a tile of rows [row0, row0+128) of an [n][cols] activation matrix; rows >= n are zero filled
-__device__ __forceinline__ void stage_rows(__half* dst, int ld, const __half* __restrict__ src, int64_t row0, int64_t n, int cols, int tid) {
+__device__ __forceinline__ void stage_rows(__half* dst, int ld, const __half* __restrict__ src, int64_t row0, int64_t n, int cols, int tid, int src_stride = 0) {
     const int cpr = cols / 8;
+    if (src_stride == 0) src_stride = cols;
     for (int i = tid; i < kTile * cpr; i += kMlpThreads) {
         const int r = i / cpr, c = (i % cpr) * 8;
         int4 v = make_int4(0, 0, 0, 0);
-        if (row0 + r < n) v = __ldg(reinterpret_cast<const int4*>(src + (size_t)(row0 + r) * cols + c));
+        if (row0 + r < n) v = __ldg(reinterpret_cast<const int4*>(src + (size_t)(row0 + r) * src_stride + c));
         *reinterpret_cast<int4*>(dst + r * ld + c) = v;
     }
 }
@@ -124,8 +126,10 @@ __device__ __forceinline__ float out_activation(float x, int act) {
 
 template <int WIDTH, int K_IN>
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_fwd_kernel(const __half* __restrict__ in, const __half* __restrict__ W, int n_hidden, int out_act, int64_t n,
-               __half* __restrict__ out, __half* __restrict__ acts) {
+mlp_fwd_kernel(const __half* __restrict__ in, int in_stride, const __half* __restrict__ W, int n_hidden, int out_act, int64_t n_max,
+               const int32_t* __restrict__ n_dev, __half* __restrict__ out, int out_stride, float* __restrict__ out_rgb32,
+               __half* __restrict__ acts) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_max) : n_max;
     using L = MlpLayout<WIDTH, K_IN>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __half* sW = reinterpret_cast<__half*>(smem_raw);
@@ -136,7 +140,7 @@ mlp_fwd_kernel(const __half* __restrict__ in, const __half* __restrict__ W, int 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kTile;
         __syncthreads();  // previous tile fully consumed (and weights staged)
-        stage_rows(sIn, L::ldIn, in, row0, n, K_IN, tid);
+        stage_rows(sIn, L::ldIn, in, row0, n, K_IN, tid, in_stride);
         __syncthreads();
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
@@ -155,7 +159,7 @@ mlp_fwd_kernel(const __half* __restrict__ in, const __half* __restrict__ W, int 
                 zero_acc(c);
                 gemm_nk<WIDTH / 8, WIDTH / 16>(c, aH, sW + L::wh + (l - 1) * WIDTH * L::ldH, L::ldH, lane);
                 relu_pack(c, aH);
-                if (acts) store_frag_rows<WIDTH / 16>(acts + (size_t)l * n * WIDTH, WIDTH, row_g, n, aH, lane);
+                if (acts) store_frag_rows<WIDTH / 16>(acts + (size_t)l * n_max * WIDTH, WIDTH, row_g, n, aH, lane);
             }
             float co[2][4];
             zero_acc(co);
@@ -163,12 +167,15 @@ mlp_fwd_kernel(const __half* __restrict__ in, const __half* __restrict__ W, int 
             const int t2 = (lane & 3) * 2;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                if (row_g < n)
-                    *reinterpret_cast<uint32_t*>(out + (size_t)row_g * kOutPad + nt * 8 + t2) =
-                        pack_h2(out_activation(co[nt][0], out_act), out_activation(co[nt][1], out_act));
-                if (row_g + 8 < n)
-                    *reinterpret_cast<uint32_t*>(out + (size_t)(row_g + 8) * kOutPad + nt * 8 + t2) =
-                        pack_h2(out_activation(co[nt][2], out_act), out_activation(co[nt][3], out_act));
+                const uint32_t lo = pack_h2(out_activation(co[nt][0], out_act), out_activation(co[nt][1], out_act));
+                const uint32_t hi = pack_h2(out_activation(co[nt][2], out_act), out_activation(co[nt][3], out_act));
+                if (row_g < n) *reinterpret_cast<uint32_t*>(out + (size_t)row_g * out_stride + nt * 8 + t2) = lo;
+                if (row_g + 8 < n) *reinterpret_cast<uint32_t*>(out + (size_t)(row_g + 8) * out_stride + nt * 8 + t2) = hi;
+                if (out_rgb32 && nt == 0 && t2 < 4) {  // fp32 copy of outputs 0..2 (the values as rounded to fp16)
+                    const float2 flo = __half22float2(*reinterpret_cast<const __half2*>(&lo)), fhi = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                    if (row_g < n) { out_rgb32[3 * row_g + t2] = flo.x; if (t2 == 0) out_rgb32[3 * row_g + 1] = flo.y; }
+                    if (row_g + 8 < n) { out_rgb32[3 * (row_g + 8) + t2] = fhi.x; if (t2 == 0) out_rgb32[3 * (row_g + 8) + 1] = fhi.y; }
+                }
             }
         }
     }
@@ -228,8 +235,10 @@ __device__ __forceinline__ void wgrad_flush(float (&acc)[MT][NT][4], float* __re
 
 template <int WIDTH, int K_IN, bool FLUSH>
 __global__ void __launch_bounds__(kMlpThreads)
-mlp_bwd_kernel(const __half* __restrict__ dOut, const __half* __restrict__ in, const __half* __restrict__ acts, const __half* __restrict__ outv,
-               const __half* __restrict__ W, int n_hidden, int out_act, int64_t n, __half* __restrict__ dIn, float* __restrict__ dW) {
+mlp_bwd_kernel(const __half* __restrict__ dOut, const __half* __restrict__ in, int in_stride, const __half* __restrict__ acts,
+               const __half* __restrict__ outv, int out_stride, const __half* __restrict__ W, int n_hidden, int out_act, int64_t n_max,
+               const int32_t* __restrict__ n_dev, __half* __restrict__ dIn, int din_stride, float* __restrict__ dW) {
+    const int64_t n = n_dev ? min((int64_t)*n_dev, n_max) : n_max;
     using L = MlpLayout<WIDTH, K_IN>;
     constexpr int MT = WIDTH / 64;  // m16 tiles of dW rows per warp (4 warps split WIDTH rows)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,8 +259,8 @@ mlp_bwd_kernel(const __half* __restrict__ dOut, const __half* __restrict__ in, c
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kTile;
         __syncthreads();
-        stage_rows(sIn, L::ldIn, in, row0, n, K_IN, tid);
-        for (int l = 0; l < n_hidden; ++l) stage_rows(sAct + l * kTile * L::ldH, L::ldH, acts + (size_t)l * n * WIDTH, row0, n, WIDTH, tid);
+        stage_rows(sIn, L::ldIn, in, row0, n, K_IN, tid, in_stride);
+        for (int l = 0; l < n_hidden; ++l) stage_rows(sAct + l * kTile * L::ldH, L::ldH, acts + (size_t)l * n_max * WIDTH, row0, n, WIDTH, tid);
         // dL/dz of the output layer: dOut (* sigmoid' when the output activation is a sigmoid)
         for (int i = tid; i < kTile * kOutPad / 2; i += kMlpThreads) {
             const int r = i / (kOutPad / 2), c = (i % (kOutPad / 2)) * 2;
@@ -259,11 +268,11 @@ mlp_bwd_kernel(const __half* __restrict__ dOut, const __half* __restrict__ in, c
             if (row0 + r < n) {
                 v = *reinterpret_cast<const __half2*>(dOut + (size_t)(row0 + r) * kOutPad + c);
                 if (out_act == MFN_ACT_SIGMOID) {
-                    const float2 y = __half22float2(*reinterpret_cast<const __half2*>(outv + (size_t)(row0 + r) * kOutPad + c));
+                    const float2 y = __half22float2(*reinterpret_cast<const __half2*>(outv + (size_t)(row0 + r) * out_stride + c));
                     const float2 g = __half22float2(v);
                     v = __floats2half2_rn(g.x * y.x * (1.f - y.x), g.y * y.y * (1.f - y.y));
                 } else if (out_act == MFN_ACT_EXP) {
-                    const float2 y = __half22float2(*reinterpret_cast<const __half2*>(outv + (size_t)(row0 + r) * kOutPad + c));
+                    const float2 y = __half22float2(*reinterpret_cast<const __half2*>(outv + (size_t)(row0 + r) * out_stride + c));
                     const float2 g = __half22float2(v);
                     v = __floats2half2_rn(g.x * y.x, g.y * y.y);
                 }
@@ -295,8 +304,8 @@ mlp_bwd_kernel(const __half* __restrict__ dOut, const __half* __restrict__ in, c
                 const int t2 = (lane & 3) * 2;
 #pragma unroll
                 for (int nt = 0; nt < K_IN / 8; ++nt) {
-                    if (row_g < n) *reinterpret_cast<uint32_t*>(dIn + (size_t)row_g * K_IN + nt * 8 + t2) = pack_h2(ci[nt][0], ci[nt][1]);
-                    if (row_g + 8 < n) *reinterpret_cast<uint32_t*>(dIn + (size_t)(row_g + 8) * K_IN + nt * 8 + t2) = pack_h2(ci[nt][2], ci[nt][3]);
+                    if (row_g < n) *reinterpret_cast<uint32_t*>(dIn + (size_t)row_g * din_stride + nt * 8 + t2) = pack_h2(ci[nt][0], ci[nt][1]);
+                    if (row_g + 8 < n) *reinterpret_cast<uint32_t*>(dIn + (size_t)(row_g + 8) * din_stride + nt * 8 + t2) = pack_h2(ci[nt][2], ci[nt][3]);
                 }
             }
         }
@@ -327,22 +336,25 @@ static int max_ctas_per_sm(K kernel, size_t smem) {
 }
 
 template <int WIDTH, int K_IN>
-static int launch_fwd(const __half* in, const __half* W, int n_hidden, int out_act, int64_t n, __half* out, __half* acts, cudaStream_t st) {
-    const size_t smem = MlpLayout<WIDTH, K_IN>::fwd_bytes(n_hidden);
+static int launch_fwd(const MlpFwdArgs& a, cudaStream_t st) {
+    const size_t smem = MlpLayout<WIDTH, K_IN>::fwd_bytes(a.n_hidden);
     static int per_sm = max_ctas_per_sm(mlp_fwd_kernel<WIDTH, K_IN>, MlpLayout<WIDTH, K_IN>::fwd_bytes(2));
-    const int64_t tiles = ceil_div(n, kTile);
+    const int64_t tiles = ceil_div(a.n_max, kTile);
     const int grid = (int)(tiles < (int64_t)per_sm * kNumSMs ? tiles : (int64_t)per_sm * kNumSMs);
-    mlp_fwd_kernel<WIDTH, K_IN><<<grid, kMlpThreads, smem, st>>>(in, W, n_hidden, out_act, n, out, acts);
+    ProfScope ps(a.tag ? a.tag : "mlp_fwd", st);
+    mlp_fwd_kernel<WIDTH, K_IN><<<grid, kMlpThreads, smem, st>>>(a.in, a.in_stride, a.W, a.n_hidden, a.out_act, a.n_max, a.n_dev, a.out,
+                                                              a.out_stride ? a.out_stride : kOutPad, a.out_rgb32, a.acts);
     return check_launch("mfn_mlp_fwd", st);
 }
 template <int WIDTH, int K_IN, bool FLUSH>
-static int launch_bwd(const __half* dOut, const __half* in, const __half* acts, const __half* outv, const __half* W, int n_hidden, int out_act,
-                      int64_t n, __half* dIn, float* dW, cudaStream_t st) {
-    const size_t smem = MlpLayout<WIDTH, K_IN>::bwd_bytes(n_hidden);
+static int launch_bwd(const MlpBwdArgs& a, cudaStream_t st) {
+    const size_t smem = MlpLayout<WIDTH, K_IN>::bwd_bytes(a.n_hidden);
     static int per_sm = max_ctas_per_sm(mlp_bwd_kernel<WIDTH, K_IN, FLUSH>, MlpLayout<WIDTH, K_IN>::bwd_bytes(2));
-    const int64_t tiles = ceil_div(n, kTile);
+    const int64_t tiles = ceil_div(a.n_max, kTile);
     const int grid = (int)(tiles < (int64_t)per_sm * kNumSMs ? tiles : (int64_t)per_sm * kNumSMs);
-    mlp_bwd_kernel<WIDTH, K_IN, FLUSH><<<grid, kMlpThreads, smem, st>>>(dOut, in, acts, outv, W, n_hidden, out_act, n, dIn, dW);
+    ProfScope ps(a.tag ? a.tag : "mlp_bwd", st);
+    mlp_bwd_kernel<WIDTH, K_IN, FLUSH><<<grid, kMlpThreads, smem, st>>>(a.dOut, a.in, a.in_stride, a.acts, a.outv, a.out_stride ? a.out_stride : kOutPad, a.W,
+                                                                     a.n_hidden, a.out_act, a.n_max, a.n_dev, a.dIn, a.din_stride ? a.din_stride : K_IN, a.dW);
     return check_launch("mfn_mlp_bwd", st);
 }
 
@@ -369,30 +381,43 @@ extern "C" int64_t mfn_mlp_param_count(int in_dim, int width, int n_hidden) {
         if (in_dim == 16) { CALL128(16) } else if (in_dim == 32) { CALL128(32) } else { CALL128(64) } \
     }
 
-extern "C" int mfn_mlp_fwd(const void* in, const void* weights, int in_dim, int width, int n_hidden, int out_act, int64_t n, void* out,
-                           void* acts, void* stream) {
-    if (!mlp_cfg_ok(in_dim, width, n_hidden, "mfn_mlp_fwd")) return MFN_ERR_ARG;
-    if (n < 0) { set_error("mfn_mlp_fwd: bad n"); return MFN_ERR_ARG; }
-    if (n == 0) return MFN_OK;
-    if (!in || !weights || !out) { set_error("mfn_mlp_fwd: null pointer"); return MFN_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-#define F64(K) return launch_fwd<64, K>((const __half*)in, (const __half*)weights, n_hidden, out_act, n, (__half*)out, (__half*)acts, st);
-#define F128(K) return launch_fwd<128, K>((const __half*)in, (const __half*)weights, n_hidden, out_act, n, (__half*)out, (__half*)acts, st);
+namespace mfn {
+int mlp_forward(const MlpFwdArgs& a, int in_dim, int width, cudaStream_t st) {
+    if (!mlp_cfg_ok(in_dim, width, a.n_hidden, "mfn_mlp_fwd")) return MFN_ERR_ARG;
+    if (a.n_max <= 0) return MFN_OK;
+#define F64(K) return launch_fwd<64, K>(a, st);
+#define F128(K) return launch_fwd<128, K>(a, st);
     MFN_MLP_DISPATCH(F64, F128)
 #undef F64
 #undef F128
 }
-
-extern "C" int mfn_mlp_bwd(const void* dL_dout, const void* in, const void* acts, const void* out, const void* weights, int in_dim, int width,
-                           int n_hidden, int out_act, int64_t n, void* dL_din, float* dW, void* stream) {
-    if (!mlp_cfg_ok(in_dim, width, n_hidden, "mfn_mlp_bwd")) return MFN_ERR_ARG;
-    if (n < 0) { set_error("mfn_mlp_bwd: bad n"); return MFN_ERR_ARG; }
-    if (n == 0) return MFN_OK;
-    if (!dL_dout || !in || !acts || !weights || !dW || (out_act != MFN_ACT_NONE && !out)) { set_error("mfn_mlp_bwd: null pointer"); return MFN_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
-#define B64(K) return launch_bwd<64, K, false>((const __half*)dL_dout, (const __half*)in, (const __half*)acts, (const __half*)out, (const __half*)weights, n_hidden, out_act, n, (__half*)dL_din, dW, st);
-#define B128(K) return launch_bwd<128, K, true>((const __half*)dL_dout, (const __half*)in, (const __half*)acts, (const __half*)out, (const __half*)weights, n_hidden, out_act, n, (__half*)dL_din, dW, st);
+int mlp_backward(const MlpBwdArgs& a, int in_dim, int width, cudaStream_t st) {
+    if (!mlp_cfg_ok(in_dim, width, a.n_hidden, "mfn_mlp_bwd")) return MFN_ERR_ARG;
+    if (a.n_max <= 0) return MFN_OK;
+#define B64(K) return launch_bwd<64, K, false>(a, st);
+#define B128(K) return launch_bwd<128, K, true>(a, st);
     MFN_MLP_DISPATCH(B64, B128)
 #undef B64
 #undef B128
+}
+}  // namespace mfn
+
+extern "C" int mfn_mlp_fwd(const void* in, const void* weights, int in_dim, int width, int n_hidden, int out_act, int64_t n, void* out,
+                           void* acts, void* stream) {
+    if (n < 0) { set_error("mfn_mlp_fwd: bad n"); return MFN_ERR_ARG; }
+    if (n > 0 && (!in || !weights || !out)) { set_error("mfn_mlp_fwd: null pointer"); return MFN_ERR_ARG; }
+    MlpFwdArgs a{};
+    a.in = (const __half*)in; a.W = (const __half*)weights; a.n_hidden = n_hidden; a.out_act = out_act; a.n_max = n;
+    a.out = (__half*)out; a.acts = (__half*)acts;
+    return mlp_forward(a, in_dim, width, (cudaStream_t)stream);
+}
+
+extern "C" int mfn_mlp_bwd(const void* dL_dout, const void* in, const void* acts, const void* out, const void* weights, int in_dim, int width,
+                           int n_hidden, int out_act, int64_t n, void* dL_din, float* dW, void* stream) {
+    if (n < 0) { set_error("mfn_mlp_bwd: bad n"); return MFN_ERR_ARG; }
+    if (n > 0 && (!dL_dout || !in || !acts || !weights || !dW || (out_act != MFN_ACT_NONE && !out))) { set_error("mfn_mlp_bwd: null pointer"); return MFN_ERR_ARG; }
+    MlpBwdArgs a{};
+    a.dOut = (const __half*)dL_dout; a.in = (const __half*)in; a.acts = (const __half*)acts; a.outv = (const __half*)out; a.W = (const __half*)weights;
+    a.n_hidden = n_hidden; a.out_act = out_act; a.n_max = n; a.dIn = (__half*)dL_din; a.dW = dW;
+    return mlp_backward(a, in_dim, width, (cudaStream_t)stream);
 }

@@ -1,0 +1,85 @@
+// Fused Adam over the flat fp32 parameter vectors (train.py:136 apex FusedAdam(lr, eps=1e-15),
+// betas (0.9, 0.999), no weight decay, bias correction on) with the AMP bookkeeping folded in: gradient unscale,
+// skip-on-overflow (GradScaler semantics), refresh of the fp16 shadow parameters the field kernels read, and
+// zeroing of the gradient buffer for the next step.  HBM-bound: 30 B/param (p,g,m,v read; p,m,v,p16 written; g zeroed).
+#include "common.cuh"
+#include "../../include/mfnerf_b200.h"
+
+namespace mfn {
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, __half* __restrict__ p_h, int64_t n,
+            float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale, const int32_t* __restrict__ skip_flag, int zero_grad) {
+    const bool skip = skip_flag && *skip_flag != 0;
+    const int64_t n4 = n / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 gp = reinterpret_cast<float4*>(g)[i];
+        if (!skip) {
+            float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+            float* P = &pp.x; float* G = &gp.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = G[k] * grad_scale;
+                M[k] = beta1 * M[k] + (1.f - beta1) * gr;
+                V[k] = beta2 * V[k] + (1.f - beta2) * gr * gr;
+                P[k] -= lr * (M[k] / bc1) / (sqrtf(V[k] / bc2) + eps);
+            }
+            reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+            if (p_h) {
+                __half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
+                reinterpret_cast<uint2*>(p_h)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            }
+        }
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail (n % 4)
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (!skip) {
+            const float gr = g[i] * grad_scale;
+            const float mi = beta1 * m[i] + (1.f - beta1) * gr, vi = beta2 * v[i] + (1.f - beta2) * gr * gr;
+            m[i] = mi; v[i] = vi;
+            const float pi = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+            p[i] = pi;
+            if (p_h) p_h[i] = __float2half_rn(pi);
+        }
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+
+__global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
+}
+
+}  // namespace mfn
+
+using namespace mfn;
+
+extern "C" int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int step, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream) {
+    if (n < 0 || step < 1) { set_error("mfn_adam_step: bad argument"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("mfn_adam_step: null pointer"); return MFN_ERR_ARG; }
+    if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) || ((uintptr_t)params_h & 7)) {
+        set_error("mfn_adam_step: buffers must be 16-byte aligned"); return MFN_ERR_ARG;
+    }
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    int64_t blocks = ceil_div(n / 4 + 1, 256);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    ProfScope ps("adam", (cudaStream_t)stream);
+    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_h, n, lr, beta1, beta2, eps, bc1,
+                                                                    bc2, grad_scale, skip_flag, zero_grad);
+    return check_launch("mfn_adam_step", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!src || !dst))) { set_error("mfn_cast_f32_to_f16: bad argument"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    int64_t blocks = ceil_div(n, 256);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    cast_f32_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, n);
+    return check_launch("mfn_cast_f32_to_f16", (cudaStream_t)stream);
+}

@@ -27,11 +27,13 @@ _C = {
 
 
 def _ctype(decl: str):
-    decl = decl.strip()
+    """C type text of one parameter / return value -> ctypes type (pointers are opaque void*)"""
+    decl = decl.replace("const", " ").strip()
     if "*" in decl:
-        return ctypes.c_char_p if decl.startswith("const char") and decl.endswith("*") and "(" not in decl and decl.count("*") == 1 and "char" in decl.split("*")[0] else ctypes.c_void_p
-    base = decl.replace("const", "").split()[0]
-    return _C[base]
+        return ctypes.c_char_p if decl.split("*")[0].strip() == "char" else ctypes.c_void_p
+    if decl == "void":
+        return None
+    return _C[decl.split()[0]]
 
 
 def declared_functions(header_path: str = HEADER_PATH):
@@ -39,19 +41,15 @@ def declared_functions(header_path: str = HEADER_PATH):
     text = open(header_path).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = {}
-    for m in re.finditer(r"(const char\*|int64_t|int|void)\s+(mfn_\w+)\s*\(([^)]*)\)\s*;", text):
-        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+    for m in re.finditer(r"^([A-Za-z_][\w \*]*?)\s*\b(mfn_\w+)\s*\(([^)]*)\)\s*;", text, flags=re.M):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
         argtypes = []
         if args and args != "void":
             for a in args.split(","):
                 a = a.strip()
-                # drop the parameter name
-                a_type = a.rsplit(" ", 1)[0] if not a.endswith("*") else a
-                if "*" in a:
-                    a_type = a[: a.rindex("*") + 1]
+                a_type = a[: a.rindex("*") + 1] if "*" in a else a.rsplit(" ", 1)[0]
                 argtypes.append(_ctype(a_type))
-        restype = {"const char*": ctypes.c_char_p, "int64_t": ctypes.c_int64, "int": ctypes.c_int, "void": None}[ret]
-        out[name] = (restype, argtypes)
+        out[name] = (_ctype(ret), argtypes)
     return out
 
 

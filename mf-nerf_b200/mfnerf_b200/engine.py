@@ -1,0 +1,344 @@
+"""Sync-free training / rendering engine: the reference's `training_step` (train.py:164-190) and
+`render(test_time=True)` (rendering.py:46-118) driven directly through the C ABI, without autograd and without
+host synchronisation inside a step, so the whole step can be replayed as one CUDA graph.
+
+Step = [AABB + near clamp] -> march (count / scan / write) -> field fwd -> composite fw -> loss (+ distortion)
+       -> composite bw -> field bwd -> [all-reduce of the flat gradient when world_size > 1] -> fused Adam,
+with `update_density_grid` (networks.py:242-271) every 16 steps.  Sample arrays live in fixed-capacity buffers and every
+kernel reads the live sample count from device memory.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, field_ops
+from ._lib import call, ptr, stream_ptr
+
+MAX_SAMPLES = 1024          # rendering.py:7
+NEAR_DISTANCE = 0.01        # rendering.py:8
+G = 128                     # networks.py:27
+
+
+class FieldCfg(ctypes.Structure):
+    """mirror of `mfn_field_cfg` (include/mfnerf_b200.h)"""
+    _fields_ = [("grid", field_ops.GridCfg), ("sigma_width", ctypes.c_int32), ("sigma_hidden", ctypes.c_int32),
+                ("rgb_width", ctypes.c_int32), ("rgb_hidden", ctypes.c_int32), ("rgb_act", ctypes.c_int32),
+                ("xyz_min", ctypes.c_float * 3), ("xyz_max", ctypes.c_float * 3)]
+
+
+def make_field_cfg(scale, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, rgb_act="Sigmoid", grid="Hash",
+                   n_tables=1):
+    b = float(np.exp(np.log(N_max * scale / N_min) / (L - 1)))       # networks.py:33
+    cfg = FieldCfg()
+    cfg.grid = field_ops.make_grid_cfg(L, F, log2_T, N_min, b, grid, n_tables)
+    cfg.sigma_width, cfg.sigma_hidden = 64, 1
+    cfg.rgb_width, cfg.rgb_hidden, cfg.rgb_act = int(rgb_channels), int(rgb_layers), field_ops.ACT[rgb_act]
+    for k in range(3):
+        cfg.xyz_min[k] = -scale; cfg.xyz_max[k] = scale
+    return cfg
+
+
+def _pad(n, m=8):
+    return (n + m - 1) // m * m
+
+
+class NGPEngine:
+    def __init__(self, scale=0.5, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, n_rays=8192,
+                 device="cuda", lr=1e-2, loss_scale=1024.0, distortion_w=0.0, lambda_opacity=1e-3, sample_capacity=None, seed=1337,
+                 exp_step_factor=None, T_threshold=1e-4, world_size=1, process_group=None):
+        self.dev = torch.device(device)
+        self.scale, self.n_rays = float(scale), int(n_rays)
+        self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)                     # networks.py:26
+        self.esf = (1.0 / 256 if scale > 0.5 else 0.0) if exp_step_factor is None else float(exp_step_factor)   # train.py:100-101
+        self.bg = (ctypes.c_float * 3)(*([1.0, 1.0, 1.0] if self.esf == 0 else [0.0, 0.0, 0.0]))           # rendering.py:153-161
+        self.cfg = make_field_cfg(scale, L, F, log2_T, N_min, N_max, rgb_channels, rgb_layers)
+        self.lr, self.loss_scale, self.T_thr = lr, float(loss_scale), float(T_threshold)
+        self.distortion_w, self.lambda_opacity = float(distortion_w), float(lambda_opacity)
+        self.world_size, self.pg = world_size, process_group
+        entries, *_ = field_ops.grid_layout(self.cfg.grid)
+        self.n_mlp1 = 64 * 32 + 16 * 64
+        self.n_xyz = self.n_mlp1 + entries * F
+        self.n_rgb = field_ops.mlp_param_count(32, rgb_channels, rgb_layers)
+        self.off_rgb = _pad(self.n_xyz)
+        self.n_params = self.off_rgb + _pad(self.n_rgb)
+        d = self.dev
+        g = torch.Generator().manual_seed(seed)
+        p = torch.zeros(self.n_params)
+        from tinycudann import _init_mlp
+        _init_mlp(p[:self.n_mlp1], 32, 64, 1, 16, g)
+        p[self.n_mlp1:self.n_xyz].uniform_(-1e-4, 1e-4, generator=g)
+        _init_mlp(p[self.off_rgb:self.off_rgb + self.n_rgb], 32, rgb_channels, rgb_layers, 16, g)
+        self.params = p.to(d)
+        self.params_h = self.params.half()
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.step_count = 0
+        # occupancy grid (train.py:78-81, networks.py:27-29)
+        self.density_grid = torch.zeros(self.cascades, G ** 3, device=d)
+        self.density_bitfield = torch.zeros(self.cascades * G ** 3 // 8, dtype=torch.uint8, device=d)
+        from .synthetic import morton_order_coords
+        self.cell_coords = torch.from_numpy(morton_order_coords(G)).to(d)      # row m = coords of morton index m
+        # per-ray buffers
+        R = self.n_rays
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=d)
+        self.rays = f(3, R, 3)                                   # packed [rays_o | rays_d | target]: one copy per step
+        self.rays_o, self.rays_d, self.target = self.rays[0], self.rays[1], self.rays[2]
+        self.hit_cnt = torch.empty(R, dtype=torch.int32, device=d)
+        self.hits_t = f(R, 1, 2); self.hits_idx = torch.empty(R, 1, dtype=torch.int64, device=d)
+        self.noise = f(R)
+        self.rays_a = torch.empty(R, 3, dtype=torch.int64, device=d)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=d)
+        self.total_samples = torch.empty(R, dtype=torch.int64, device=d)
+        self.opacity, self.depth, self.rgb, self.rgb_final = f(R), f(R), f(R, 3), f(R, 3)
+        self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), torch.zeros(R, device=d), f(R, 3)
+        self.dist_loss, self.dL_ddist = f(R), f(R)
+        self.loss_terms = torch.zeros(3, device=d)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
+        self.center = torch.zeros(1, 3, device=d); self.half_size = torch.full((1, 3), self.scale, device=d)
+        # per-sample buffers at fixed capacity
+        self.cap = int(sample_capacity) if sample_capacity else R * MAX_SAMPLES
+        S = self.cap
+        self.xyzs, self.dirs, self.deltas, self.ts = f(S, 3), f(S, 3), f(S), f(S)
+        self.sigmas, self.rgbs, self.ws = f(S), f(S, 3), f(S)
+        self.dL_dsigmas, self.dL_drgbs, self.dL_dws = f(S), f(S, 3), torch.zeros(S, device=d)
+        self.ws_incl, self.wts_incl = (f(S), f(S)) if self.distortion_w > 0 else (None, None)
+        self.march_ws = torch.empty(_lib.lib.mfn_march_train_workspace_bytes(R, MAX_SAMPLES), dtype=torch.uint8, device=d)
+        self.field_ws = torch.empty(_lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), S, 1), dtype=torch.uint8, device=d)
+        self._graph = None
+        self._cells_ws = None
+        self.graph_replays = 0
+        self.launches_per_forward_backward = 0
+        self.samples_acc = torch.zeros(1, dtype=torch.float64, device=d)   # running sum of marched samples (train/rm_s numerator)
+        self.fixed_noise = None     # tests: jitter noise supplied by the caller instead of drawn per step
+
+    # ------------------------------------------------------------------------------------------------ views
+    @property
+    def xyz_params_h(self):
+        return self.params_h[:self.n_xyz]
+
+    @property
+    def rgb_params_h(self):
+        return self.params_h[self.off_rgb:self.off_rgb + self.n_rgb]
+
+    def state_dict(self):
+        """reference checkpoint keys (utils.py / SURVEY section 5): flat fp32 tcnn parameter vectors + occupancy bitfield"""
+        return {"xyz_encoder.params": self.params[:self.n_xyz].clone(), "rgb_net.params": self.params[self.off_rgb:self.off_rgb + self.n_rgb].clone(),
+                "dir_encoder.params": torch.zeros(0, device=self.dev), "density_bitfield": self.density_bitfield.clone(),
+                "density_grid": self.density_grid.clone()}
+
+    def load_state_dict(self, sd):
+        self.params[:self.n_xyz].copy_(sd["xyz_encoder.params"]); self.params[self.off_rgb:self.off_rgb + self.n_rgb].copy_(sd["rgb_net.params"])
+        self.params_h.copy_(self.params)
+        if "density_bitfield" in sd:
+            self.density_bitfield.copy_(sd["density_bitfield"])
+        if "density_grid" in sd:
+            self.density_grid.copy_(sd["density_grid"])
+
+    # ------------------------------------------------------------------------------------------------ field queries
+    @torch.no_grad()
+    def field(self, xyzs, dirs):
+        """NGP.forward (networks.py:134-155) without autograd: (n,3),(n,3) -> sigmas (n) f32, rgbs (n,3) f32"""
+        n = xyzs.shape[0]
+        cfg = ctypes.byref(self.cfg)
+        need = _lib.lib.mfn_field_workspace_bytes(cfg, n, 0)
+        if self._cells_ws is None or self._cells_ws.numel() < need:
+            self._cells_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        sig = torch.empty(n, device=self.dev); col = torch.empty(n, 3, device=self.dev)
+        call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(xyzs.contiguous()), ptr(dirs.contiguous()), n, None,
+             ptr(sig), ptr(col), ptr(self._cells_ws), self._cells_ws.numel(), stream_ptr(self.dev))
+        return sig, col
+
+    # ------------------------------------------------------------------------------------------------ occupancy grid
+    @torch.no_grad()
+    def density(self, xyz):
+        """NGP.density (networks.py:96-110) for (n,3) world positions -> sigmas (n)"""
+        n = xyz.shape[0]
+        need = _lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), n, 0)
+        ws = self.field_ws
+        if need > ws.numel():
+            if self._cells_ws is None or self._cells_ws.numel() < need:
+                self._cells_ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+            ws = self._cells_ws
+        out = torch.empty(n, device=self.dev)
+        call("mfn_density_fwd", ctypes.byref(self.cfg), ptr(self.xyz_params_h), ptr(xyz), n, None, ptr(out), ptr(ws), ws.numel(), stream_ptr(self.dev))
+        return out
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95):
+        """networks.py:242-271 without its host syncs (nonzero / .item()): occupied cells are drawn with a cumsum +
+        searchsorted instead of nonzero, and the packbits threshold min(mean, thr) is read on the device."""
+        d = self.dev
+        tmp = torch.zeros_like(self.density_grid)
+        M = G ** 3 // 4
+        for c in range(self.cascades):
+            if warmup:                                    # get_all_cells (networks.py:157-168)
+                idx = None
+                coords = self.cell_coords
+            else:                                         # sample_uniform_and_occupied_cells (networks.py:170-197)
+                coords1 = torch.randint(G, (M, 3), dtype=torch.int32, device=d)
+                idx1 = torch.empty(M, dtype=torch.int32, device=d)
+                call("mfn_morton3d", ptr(coords1), M, ptr(idx1), stream_ptr(d))
+                occ = (self.density_grid[c] > density_threshold)
+                cs = torch.cumsum(occ, 0, dtype=torch.int32)
+                k = (torch.rand(M, device=d) * cs[-1]).to(torch.int32)
+                idx2 = torch.searchsorted(cs, k, right=True).clamp_(max=G ** 3 - 1).to(torch.int32)
+                idx = torch.cat([idx1, idx2]).long()
+                coords = self.cell_coords[idx]
+            s = min(2.0 ** (c - 1), self.scale)
+            half = s / G
+            xyz = (coords.float() / (G - 1) * 2 - 1) * (s - half)
+            xyz += (torch.rand_like(xyz) * 2 - 1) * half
+            sig = self.density(xyz.contiguous())
+            if idx is None:
+                tmp[c] = sig
+            else:
+                tmp[c, idx] = sig
+        self.density_grid = torch.where(self.density_grid < 0, self.density_grid, torch.maximum(self.density_grid * decay, tmp))
+        pos = self.density_grid > 0
+        mean = (torch.where(pos, self.density_grid, torch.zeros_like(self.density_grid)).sum() / pos.sum().clamp_(min=1)).reshape(1).float()
+        self._mean_density = mean
+        call("mfn_packbits_dev_thr", ptr(self.density_grid), self.density_bitfield.numel(), float(density_threshold), ptr(mean),
+             ptr(self.density_bitfield), stream_ptr(d))
+
+    # ------------------------------------------------------------------------------------------------ training step
+    def _forward_backward(self):
+        """everything between "rays are in self.rays_o/d/target" and "self.grads holds loss_scale * dL/dparams"; no host sync"""
+        d, st, R, S = self.dev, stream_ptr(self.dev), self.n_rays, self.cap
+        cfg = ctypes.byref(self.cfg)
+        call("mfn_ray_aabb_intersect", ptr(self.rays_o), ptr(self.rays_d), ptr(self.center), ptr(self.half_size), R, 1, 1, ptr(self.hit_cnt),
+             ptr(self.hits_t), ptr(self.hits_idx), st)
+        call("mfn_clamp_near", ptr(self.hits_t), R, NEAR_DISTANCE, st)
+        if self.fixed_noise is None:
+            self.noise.uniform_(0, 1)                      # custom_functions.py:83
+        else:
+            self.noise.copy_(self.fixed_noise)
+        call("mfn_raymarching_train", ptr(self.rays_o), ptr(self.rays_d), ptr(self.hits_t), ptr(self.density_bitfield), self.cascades, self.scale,
+             self.esf, ptr(self.noise), G, MAX_SAMPLES, R, S, ptr(self.rays_a), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.ts),
+             ptr(self.counter), ptr(self.march_ws), self.march_ws.numel(), st)
+        self.samples_acc.add_(self.counter[0])
+        n_dev = ptr(self.counter)
+        call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), ptr(self.dirs), S, n_dev, ptr(self.sigmas),
+             ptr(self.rgbs), ptr(self.field_ws), self.field_ws.numel(), st)
+        call("mfn_composite_train_fw", ptr(self.sigmas), ptr(self.rgbs), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), self.T_thr, R, S,
+             ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rgb), ptr(self.ws), st)
+        dist = None
+        if self.distortion_w > 0:
+            call("mfn_distortion_loss_fw", ptr(self.ws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), R, S, ptr(self.dist_loss), ptr(self.ws_incl),
+                 ptr(self.wts_incl), st)
+            dist = self.dist_loss
+        self.loss_terms.zero_()
+        call("mfn_nerf_loss_fwbw", ptr(self.rgb), ptr(self.opacity), ptr(self.target), ptr(dist), R, self.bg, self.lambda_opacity, self.distortion_w, 1.0,
+             ptr(self.dL_drgb), ptr(self.dL_dopacity), ptr(self.dL_ddist) if dist is not None else None, ptr(self.rgb_final), ptr(self.loss_terms), st)
+        if dist is not None:
+            call("mfn_distortion_loss_bw", ptr(self.dL_ddist), ptr(self.ws_incl), ptr(self.wts_incl), ptr(self.ws), ptr(self.deltas), ptr(self.ts),
+                 ptr(self.rays_a), R, S, ptr(self.dL_dws), st)
+        call("mfn_composite_train_bw", ptr(self.dL_dopacity), ptr(self.dL_ddepth), ptr(self.dL_drgb), ptr(self.dL_dws), ptr(self.sigmas), ptr(self.rgbs),
+             ptr(self.ws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rgb), self.T_thr, R, S,
+             ptr(self.dL_dsigmas), ptr(self.dL_drgbs), st)
+        self.overflow.zero_()
+        call("mfn_field_bwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
+             self.loss_scale, ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
+
+    def _optimizer_step(self, lr=None):
+        self.step_count += 1
+        call("mfn_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
+             float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, 1.0 / (self.loss_scale * self.world_size), ptr(self.overflow), 1,
+             stream_ptr(self.dev))
+
+    def capture(self):
+        """capture _forward_backward into a CUDA graph (call after at least one eager step)"""
+        torch.cuda.synchronize(self.dev)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._forward_backward()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.grads.zero_()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.lib.mfn_launch_count()
+        with torch.cuda.graph(g):
+            self._forward_backward()
+        self.launches_per_forward_backward = int(_lib.lib.mfn_launch_count() - l0)
+        self.grads.zero_()
+        self._graph = g
+
+    def train_step(self, rays_o=None, rays_d=None, target=None, lr=None, global_step=None):
+        """one reference training_step (train.py:164-190).  Inputs (device tensors) are copied into the engine's static buffers."""
+        if global_step is None:
+            global_step = self.step_count
+        if global_step % 16 == 0:                                                            # train.py:165-168
+            self.update_density_grid(warmup=global_step < 256)
+        if rays_o is not None:
+            self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
+        self._run_forward_backward()
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        self._optimizer_step(lr)
+
+    def _run_forward_backward(self):
+        if self._graph is not None:
+            self._graph.replay()
+            self.graph_replays += 1
+        else:
+            self._forward_backward()
+
+    def train_step_packed(self, batch, lr=None, global_step=None):
+        """as train_step, with the step's rays in ONE (3, R, 3) float32 tensor [rays_o | rays_d | target] -- device memory or pinned
+        host memory (then this is the step's only host-to-device copy)."""
+        if global_step is None:
+            global_step = self.step_count
+        if global_step % 16 == 0:
+            self.update_density_grid(warmup=global_step < 256)
+        self.rays.copy_(batch, non_blocking=True)
+        self._run_forward_backward()
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        self._optimizer_step(lr)
+
+    def repack_bitfield(self, threshold):
+        """density_bitfield <- density_grid > threshold (vren.packbits, raymarching.cu:122-161)"""
+        call("mfn_packbits", ptr(self.density_grid), 0, self.density_bitfield.numel(), float(threshold), ptr(self.density_bitfield), stream_ptr(self.dev))
+
+    # ------------------------------------------------------------------------------------------------ test-time rendering
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4):
+        """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples)"""
+        import vren
+        d = self.dev
+        N = rays_o.shape[0]
+        _, hits_t, _ = vren.ray_aabb_intersect(rays_o, rays_d, self.center, self.half_size, 1)
+        hits_t = hits_t[:, 0].contiguous()
+        call("mfn_clamp_near", ptr(hits_t), N, NEAR_DISTANCE, stream_ptr(d))
+        opacity = torch.zeros(N, device=d); depth = torch.zeros(N, device=d); rgb = torch.zeros(N, 3, device=d)
+        alive = torch.arange(N, device=d)
+        samples = total = 0
+        min_samples = 1 if self.esf == 0 else 4
+        cfg = ctypes.byref(self.cfg)
+        while samples < max_samples:
+            n_alive = alive.shape[0]
+            if n_alive == 0:
+                break
+            ns = max(min(N // n_alive, 64), min_samples)
+            samples += ns
+            xyzs, dirs, deltas, ts, n_eff = vren.raymarching_test(rays_o, rays_d, hits_t, alive, self.density_bitfield, self.cascades, self.scale,
+                                                                  self.esf, G, MAX_SAMPLES, ns)
+            total += n_eff.sum()
+            n = n_alive * ns
+            need = _lib.lib.mfn_field_workspace_bytes(cfg, n, 0)
+            if self._cells_ws is None or self._cells_ws.numel() < need:
+                self._cells_ws = torch.empty(need, dtype=torch.uint8, device=d)
+            sig = torch.empty(n, device=d); col = torch.empty(n, 3, device=d)
+            # padded (all-zero) rows are evaluated too and then ignored by the compositor via N_eff -- cheaper than the
+            # reference's boolean-mask gather/scatter round trip (rendering.py:91-97) and free of its host syncs
+            dirs_v = dirs.view(-1, 3)
+            call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(xyzs), ptr(dirs_v), n, None, ptr(sig), ptr(col),
+                 ptr(self._cells_ws), self._cells_ws.numel(), stream_ptr(d))
+            vren.composite_test_fw(sig.view(n_alive, ns), col.view(n_alive, ns, 3), deltas, ts, hits_t, alive, T_threshold, n_eff, opacity, depth, rgb)
+            alive = alive[alive >= 0]
+        bg = torch.tensor(list(self.bg), device=d)
+        rgb = rgb + bg * (1 - opacity)[:, None]
+        return {"rgb": rgb, "depth": depth, "opacity": opacity, "total_samples": total}
