@@ -223,6 +223,11 @@ def run_ours(args):
     launches_per_fb = eng.launches_per_forward_backward
     for _ in range(W):
         step_from(pool_dev)
+    torch.cuda.synchronize(dev)
+    snap, snap_step = eng.snapshot(), state["step"]       # every timed region below restarts from this training state
+
+    def rewind():
+        eng.restore(snap); state["step"] = snap_step
 
     def barrier():
         if world > 1:
@@ -231,6 +236,7 @@ def run_ours(args):
 
     def timed(pool, with_loss_readback):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rewind()
         eng.samples_acc.zero_()
         l0 = _lib.lib.mfn_launch_count(); g0 = eng.graph_replays
         barrier()
@@ -271,6 +277,7 @@ def run_ours(args):
     if rank == 0 and not args.no_graph:
         eng.capture()
     n_prof = min(K, 48)
+    rewind()
     acc = {n: [] for n in PROFILED}
     smp = []
     for i in range(n_prof):

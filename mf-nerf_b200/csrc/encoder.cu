@@ -147,38 +147,74 @@ __device__ __forceinline__ void atomic_add_vec(float* p, const float (&v)[F]) {
     }
 }
 
+// Backward.  grid.y = level (all CTAs resident at one time work on the same level's table -> L2 locality); one thread per sample,
+// so a warp holds 32 consecutive samples -- samples that follow one another along a ray.  At every level whose cell is larger
+// than the marching step, consecutive samples sit in the SAME cell and address the same 8 table entries: each run of lanes with
+// an identical cell is reduced to its head lane with a segmented shuffle reduction (warp-uniform early exit once no run is longer
+// than the shuffle distance), and only the head issues the 8 vector atomics.  On the Lego-shaped workload this removes ~2/3 of
+// the L2 reductions (measured: 213 us -> 65 us for 223k samples, tools/encbwd_bench.cu; the L2 sustains ~182 G lane-red/s).
 template <int F>
 __global__ void __launch_bounds__(256)
 grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restrict__ dL_dout, const __grid_constant__ GridMeta m,
                        float* __restrict__ dgrid, int32_t* __restrict__ overflow_flag) {
     const int64_t n = e.n_dev ? min((int64_t)*e.n_dev, e.n_max) : e.n_max;
     const int l = blockIdx.y;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float g[F];
-    bool any = false, bad = false;
-#pragma unroll
-    for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); any |= (g[f] != 0.f); bad |= !isfinite(g[f]); }
-    if (bad && overflow_flag) *overflow_flag = 1;
-    if (!any) continue;
-    float x, y, z;
-    load_pos(e, i, x, y, z);
+    const int lane = threadIdx.x & 31;
     const float s = m.scale[l];
     const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
     const bool hashed = (m.hashed >> l) & 1u;
-    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
-    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    const float wx = px - fx, wy = py - fy, wz = pz - fz;
-    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
     float* lvl = dgrid + (size_t)m.offset[l] * F;
+    const int64_t n_pad = (n + 31) / 32 * 32;   // whole warps stay in the loop (shuffles below)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        float g[F];
+        bool live = false, bad = false;
+        if (i < n) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float w = ((c & 1) ? wx : 1.f - wx) * (((c >> 1) & 1) ? wy : 1.f - wy) * ((c >> 2) ? wz : 1.f - wz);
-        const uint32_t idx = grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed);
-        float v[F];
+            for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); live |= (g[f] != 0.f); bad |= !isfinite(g[f]); }
+        }
+        if (bad && overflow_flag) *overflow_flag = 1;
+        const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
+        if (live_mask == 0) continue;
+        uint32_t gx = 0, gy = 0, gz = 0;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (live) {
+            float x, y, z;
+            load_pos(e, i, x, y, z);
+            const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            wx = px - fx; wy = py - fy; wz = pz - fz;
+            gx = (uint32_t)(int)fx; gy = (uint32_t)(int)fy; gz = (uint32_t)(int)fz;
+        }
+        float v[8][F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) v[f] = w * g[f];
-        atomic_add_vec<F>(lvl + (size_t)idx * F, v);
-    }
+        for (int c = 0; c < 8; ++c) {
+            const float w = ((c & 1) ? wx : 1.f - wx) * (((c >> 1) & 1) ? wy : 1.f - wy) * ((c >> 2) ? wz : 1.f - wz);
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[c][f] = live ? w * g[f] : 0.f;
+        }
+        // runs of consecutive live lanes in the same cell (21 bits per coordinate: resolutions up to 2^21)
+        const unsigned long long key = live ? ((unsigned long long)gx | ((unsigned long long)gy << 21) | ((unsigned long long)gz << 42)) : ~0ull;
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = live && (lane == 0 || prev != key);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const int my_run = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int other_run = __shfl_down_sync(0xffffffffu, my_run, d);
+            const bool take = live && (lane + d < 32) && ((live_mask >> ((lane + d) & 31)) & 1u) && other_run == my_run;
+            if (!__any_sync(0xffffffffu, take)) break;    // no run reaches this far: none reaches farther either
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int f = 0; f < F; ++f) { const float o = __shfl_down_sync(0xffffffffu, v[c][f], d); if (take) v[c][f] += o; }
+        }
+        if (head) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t idx = grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed);
+                atomic_add_vec<F>(lvl + (size_t)idx * F, v[c]);
+            }
+        }
     }
 }
 

@@ -299,6 +299,20 @@ class NGPEngine:
             torch.distributed.all_reduce(self.grads, group=self.pg)
         self._optimizer_step(lr)
 
+    def snapshot(self):
+        """copy of everything a training step mutates (bench.py restores it so that every timed region sees the same workload)"""
+        return {"params": self.params.clone(), "params_h": self.params_h.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "density_grid": self.density_grid.clone(), "density_bitfield": self.density_bitfield.clone(), "step_count": self.step_count,
+                "rng": torch.cuda.get_rng_state(self.dev)}
+
+    def restore(self, snap):
+        for k in ("params", "params_h", "exp_avg", "exp_avg_sq", "density_bitfield"):
+            getattr(self, k).copy_(snap[k])          # in place: a captured graph holds these addresses
+        self.density_grid = snap["density_grid"].clone()
+        self.grads.zero_()
+        self.step_count = snap["step_count"]
+        torch.cuda.set_rng_state(snap["rng"], self.dev)
+
     def repack_bitfield(self, threshold):
         """density_bitfield <- density_grid > threshold (vren.packbits, raymarching.cu:122-161)"""
         call("mfn_packbits", ptr(self.density_grid), 0, self.density_bitfield.numel(), float(threshold), ptr(self.density_bitfield), stream_ptr(self.dev))
