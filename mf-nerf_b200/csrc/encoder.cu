@@ -12,6 +12,7 @@
 // table -> L2 locality), fp32 vector atomics (red.global.add.v2.f32 on sm_100) into a dense fp32 gradient table.
 // Algorithmic bytes/sample (L=16,F=2): fwd 12 + 512 gathered + 64 written; bwd 12 + 64 + 512 scattered.
 #include "field_internal.h"
+#include "grid_common.cuh"
 #include "sh4.cuh"
 #include <math.h>
 
@@ -45,61 +46,6 @@ int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
     }
     m->offset[cfg->n_levels] = (uint32_t)off;
     return MFN_OK;
-}
-
-__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size, bool hashed) {
-    uint32_t idx;
-    if (hashed) idx = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    else idx = x + y * res + z * res * res;
-    return idx % size;
-}
-
-template <int F> struct FeatVec;
-template <> struct FeatVec<1> { using T = unsigned short; };
-template <> struct FeatVec<2> { using T = uint32_t; };
-template <> struct FeatVec<4> { using T = uint2; };
-template <> struct FeatVec<8> { using T = uint4; };
-
-template <int F>
-__device__ __forceinline__ void add_weighted(float (&acc)[F], const typename FeatVec<F>::T& raw, float w) {
-    const __half* h = reinterpret_cast<const __half*>(&raw);
-#pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = fmaf(w, __half2float(h[f]), acc[f]);
-}
-
-// interpolate one level for one sample
-template <int F>
-__device__ __forceinline__ void encode_level(const __half* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, float (&acc)[F]) {
-    const float s = m.scale[l];
-    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
-    const bool hashed = (m.hashed >> l) & 1u;
-    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
-    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    const float wx = px - fx, wy = py - fy, wz = pz - fz;
-    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-    const typename FeatVec<F>::T* lvl = reinterpret_cast<const typename FeatVec<F>::T*>(table) + m.offset[l];
-    typename FeatVec<F>::T v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        v[c] = __ldg(lvl + grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed));
-#pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float w = ((c & 1) ? wx : 1.f - wx) * (((c >> 1) & 1) ? wy : 1.f - wy) * ((c >> 2) ? wz : 1.f - wz);
-        add_weighted<F>(acc, v[c], w);
-    }
-}
-
-// sample position in [0,1]^3; with e.normalize the world position is mapped exactly like networks.py:105,
-// x = (x - xyz_min) / (xyz_max - xyz_min), in IEEE fp32
-__device__ __forceinline__ void load_pos(const EncArgs& e, int64_t i, float& x, float& y, float& z) {
-    x = e.x[3 * i]; y = e.x[3 * i + 1]; z = e.x[3 * i + 2];
-    if (e.normalize) {
-        x = __fdiv_rn(__fsub_rn(x, e.mn[0]), __fsub_rn(e.mx[0], e.mn[0]));
-        y = __fdiv_rn(__fsub_rn(y, e.mn[1]), __fsub_rn(e.mx[1], e.mn[1]));
-        z = __fdiv_rn(__fsub_rn(z, e.mn[2]), __fsub_rn(e.mx[2], e.mn[2]));
-    }
 }
 
 template <int F>
@@ -222,26 +168,6 @@ grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restri
 __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {  // body shared via sh4.cuh
     sh4_eval(x, y, z, o);
 }
-#if 0
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    o[0] = 0.28209479177387814f;
-    o[1] = -0.48860251190291987f * y;
-    o[2] = 0.48860251190291987f * z;
-    o[3] = -0.48860251190291987f * x;
-    o[4] = 1.0925484305920792f * xy;
-    o[5] = -1.0925484305920792f * yz;
-    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-    o[7] = -1.0925484305920792f * xz;
-    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-    o[10] = 2.8906114426405538f * xy * z;
-    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-    o[14] = 1.4453057213202769f * z * (x2 - y2);
-    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
-#endif
 
 __global__ void sh4_fwd_kernel(const float* __restrict__ d01, int64_t n, __half* __restrict__ out, int out_stride, int out_offset) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
