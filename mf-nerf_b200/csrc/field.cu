@@ -6,8 +6,31 @@
 // workspace; every kernel takes the sample count from device memory (n_dev) so a whole training step needs no host sync.
 #include "field_internal.h"
 #include "sh4.cuh"
+#include <stdlib.h>
 
 namespace mfn {
+
+// MFN_FIELD_IMPL=v1 selects the unfused pipeline below (kept for shapes the fused kernels do not cover and for A/B measurements)
+static bool use_fused(const mfn_field_cfg* c) {
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("MFN_FIELD_IMPL"); v1 = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
+    return !v1 && fused_field_supported(c);
+}
+
+// workspace of the fused path: [tile blobs | rgb copy (n,3) f32 | dfeats (n,32) f16 | weight-gradient partials]
+struct FusedWs { size_t blobs, rgb, dfeats, partials, total; };
+static FusedWs fused_ws(int64_t n, bool training) {
+    FusedWs w{};
+    size_t o = 0;
+    if (training) {
+        w.blobs = o; o += fused_blob_bytes(n);
+        w.rgb = o; o += (size_t)(n * 12 + 255) / 256 * 256;
+        w.dfeats = o; o += (size_t)(n * 64 + 255) / 256 * 256;
+        w.partials = o; o += (fused_partial_bytes() + 255) / 256 * 256;
+    }
+    w.total = o > 256 ? o : 256;
+    return w;
+}
 
 struct FieldWs {
     size_t feats, acts1, cat, acts2, out2, dout2, dcat, dh, dfeats, out1, total;
@@ -120,12 +143,25 @@ using namespace mfn;
 
 extern "C" int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg, int64_t n_max, int training) {
     if (field_cfg_ok(cfg, "mfn_field_workspace_bytes") != MFN_OK || n_max < 0) return -1;
-    return (int64_t)field_ws(cfg, n_max, training != 0).total;
+    const size_t v1 = field_ws(cfg, n_max, training != 0).total;
+    const size_t fz = fused_field_supported(cfg) ? fused_ws(n_max, training != 0).total : 0;
+    return (int64_t)(v1 > fz ? v1 : fz);
 }
 
 static void make_enc(EncArgs& e, const mfn_field_cfg* cfg, const float* xyzs, int64_t n_max, const int32_t* n_dev) {
     e.x = xyzs; e.normalize = true; e.n_max = n_max; e.n_dev = n_dev;
     for (int k = 0; k < 3; ++k) { e.mn[k] = cfg->xyz_min[k]; e.mx[k] = cfg->xyz_max[k]; }
+}
+
+static void make_fused(FusedArgs& f, const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, const float* dirs,
+                       int64_t n_max, const int32_t* n_dev) {
+    f = FusedArgs{};
+    f.xyzs = xyzs; f.dirs = dirs; f.n_max = n_max; f.n_dev = n_dev;
+    for (int k = 0; k < 3; ++k) { f.mn[k] = cfg->xyz_min[k]; f.mx[k] = cfg->xyz_max[k]; }
+    f.w_sigma = (const __half*)xyz_params_h;
+    f.table = f.w_sigma + 64 * 32 + 16 * 64;
+    f.w_rgb = (const __half*)rgb_params_h;
+    f.rgb_act = cfg->rgb_act;
 }
 
 extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, const float* dirs,
@@ -143,6 +179,15 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_field_fwd")) != MFN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
+    if (use_fused(cfg)) {
+        // training layout when the workspace is large enough for it (the matching mfn_field_bwd reads it), inference otherwise
+        const FusedWs fw = fused_ws(n_max, true);
+        const bool train = (size_t)workspace_bytes >= fw.total;
+        FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
+        f.sigmas = sigmas; f.rgbs = rgbs;
+        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); }
+        return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
+    }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;
     EncArgs e; make_enc(e, cfg, xyzs, n_max, n_dev);
@@ -174,6 +219,16 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_field_bwd")) != MFN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
+    if (use_fused(cfg)) {
+        const FusedWs fw = fused_ws(n_max, true);
+        if ((size_t)workspace_bytes < fw.total) { set_error("mfn_field_bwd: workspace too small"); return MFN_ERR_ARG; }
+        FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, nullptr, n_max, n_dev);
+        f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.dfeats = (__half*)(ws + fw.dfeats);
+        f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
+        if ((rc = fused_field_backward(f, cfg->rgb_hidden, d_xyz_params, d_rgb_params, st)) != MFN_OK) return rc;
+        EncArgs e; make_enc(e, cfg, xyzs, n_max, n_dev);
+        return grid_encode_backward(e, f.dfeats, m, cfg->grid.n_features, d_xyz_params + 64 * 32 + 16 * 64, overflow_flag, st);
+    }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;
     note_launch(2);  // prep_dout2 + merge_dh
@@ -210,6 +265,11 @@ extern "C" int mfn_density_fwd(const mfn_field_cfg* cfg, const void* xyz_params_
     if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_density_fwd")) != MFN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
+    if (use_fused(cfg)) {
+        FusedArgs f; make_fused(f, cfg, xyz_params_h, nullptr, xyzs, nullptr, n_max, n_dev);
+        f.sigmas = sigmas;
+        return fused_field_forward(f, m, cfg->rgb_hidden, 2, st);
+    }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;
     EncArgs e; make_enc(e, cfg, xyzs, n_max, n_dev);

@@ -1,0 +1,627 @@
+// Fused NGP field kernels for sm_100a: hash-grid gather + sigma MLP + SH + rgb MLP in ONE kernel (forward), and the whole MLP
+// backward (dgrad chain + weight gradients) in ONE kernel, on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+// Replaces, for the standard NGP shape (L*F = 32 encoded features with F = 2, 64-wide sigma net with one hidden layer, 64-wide
+// rgb net with 1 or 2 hidden layers), the v1 pipeline of field.cu (encoder kernel -> mma.sync MLP kernels with every
+// intermediate in HBM).  Semantics: models/networks.py:96-155 (NGP.density / NGP.forward), TruncExp custom_functions.py:162-173.
+//
+// Forward, one CTA = 128 samples (thread t owns sample row t == TMEM lane t), persistent over tiles, 4 CTAs / SM:
+//   gather 16 levels x 8 corners (fp32 interpolation) -> X tile [128x32] fp16 in shared memory (canonical un-swizzled core-matrix
+//   layout, umma.cuh) -> tcgen05.mma X.W1^T -> TMEM -> ReLU -> H1 tile -> mma H1.W2^T -> h (16) -> sigma = exp(h0);
+//   CAT tile = [SH4(dir) | h] -> mma CAT.W3^T -> ReLU -> mma .W4^T -> ReLU -> mma .W5^T -> sigmoid -> rgb.
+//   Nothing but xyz/dir in and sigma/rgb out touches HBM at inference.  In training the five activation tiles are also stored,
+//   as one contiguous 64 KiB blob per tile *in the shared-memory layout*, so that the backward kernel fetches a tile with a single
+//   bulk async copy (cp.async.bulk, the 1-D TMA path) and feeds it to the tensor cores without any re-staging.
+// Backward, one CTA = 128 samples, persistent, 2 CTAs / SM:
+//   dZ5 = dL/drgb * sigmoid' -> [dgrad mma -> TMEM -> ReLU mask -> dZ tile (in place of the activation it masks)] x 4 -> dX;
+//   the weight gradients dW = dZ^T.A are tcgen05 MMAs with M = 64, both operands read MN-major from the very same tiles, and
+//   they ACCUMULATE IN TMEM across all tiles of the CTA (fp32); one partial per CTA is written at the end and a small kernel reduces
+//   the partials (deterministic, no atomics).  dX (fp16, loss-scaled) goes to the hash-grid scatter kernel (encoder.cu).
+#include "field_internal.h"
+#include "grid_common.cuh"
+#include "sh4.cuh"
+#include "umma.cuh"
+
+namespace mfn {
+using namespace umma;
+
+constexpr int kFT = 128;                 // samples per tile
+// shared-memory byte offsets (both kernels): weights first, all tiles in the canonical row-core layout
+constexpr int kW1 = 0;                   // [64 x 32]
+constexpr int kW2 = kW1 + 64 * 32 * 2;   // [16 x 64]
+constexpr int kW3 = kW2 + 16 * 64 * 2;   // [64 x 32]
+constexpr int kW4 = kW3 + 64 * 32 * 2;   // [64 x 64]
+constexpr int kW5 = kW4 + 64 * 64 * 2;   // [16 x 64]
+constexpr int kWEnd = kW5 + 16 * 64 * 2; // 20480
+// saved-activation blob of one tile (== the shared-memory image of the backward kernel's tile area)
+constexpr int kBX = 0;                       // X   [128 x 32]
+constexpr int kBH1 = kBX + kFT * 32 * 2;     // H1  [128 x 64]
+constexpr int kBC = kBH1 + kFT * 64 * 2;     // CAT [128 x 32] = [SH | h]
+constexpr int kBH2 = kBC + kFT * 32 * 2;     // H2  [128 x 64]
+constexpr int kBH3 = kBH2 + kFT * 64 * 2;    // H3  [128 x 64] (rgb nets with two hidden layers)
+constexpr int kBlob = kBH3 + kFT * 64 * 2;   // 65536
+static_assert(kBlob == 65536, "blob size");
+// forward kernel shared memory: weights | X | H | CAT
+constexpr int kFwdX = kWEnd, kFwdH = kFwdX + kFT * 32 * 2, kFwdC = kFwdH + kFT * 64 * 2, kFwdSmem = kFwdC + kFT * 32 * 2;
+// backward kernel shared memory: weights | blob image | dZo [128 x 16]
+constexpr int kBwdBlob = kWEnd, kBwdDZo = kBwdBlob + kBlob, kBwdSmem = kBwdDZo + kFT * 16 * 2;
+// TMEM columns
+constexpr int kFwdCols = 128, kAccH = 0, kAccO = 64;
+constexpr int kBwdCols = 256, kAccW5 = 64, kAccW4 = 80, kAccW3 = 144, kAccW2 = 176, kAccW1 = 192;
+constexpr int kNumWg = 64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;   // 10240 weight-gradient floats per partial
+
+// global row-major [rows][cols] fp16 matrix -> row-core tile in shared memory
+__device__ __forceinline__ void stage_weight(unsigned char* dst, const __half* __restrict__ src, int rows, int cols, int tid, int nthreads) {
+    const int cpr = cols >> 3;
+    for (int q = tid; q < rows * cpr; q += nthreads) {
+        const int r = q / cpr, c = (q % cpr) << 3;
+        *reinterpret_cast<uint4*>(dst + tile_off(r, c, cols)) = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * cols + c));
+    }
+}
+
+template <int NH2>
+__device__ __forceinline__ void stage_all_weights(unsigned char* smem, const FusedArgs& a, int tid, int nthreads, bool rgb) {
+    stage_weight(smem + kW1, a.w_sigma, 64, 32, tid, nthreads);
+    stage_weight(smem + kW2, a.w_sigma + 64 * 32, 16, 64, tid, nthreads);
+    if (rgb) {
+        stage_weight(smem + kW3, a.w_rgb, 64, 32, tid, nthreads);
+        if (NH2 == 2) stage_weight(smem + kW4, a.w_rgb + 64 * 32, 64, 64, tid, nthreads);
+        stage_weight(smem + kW5, a.w_rgb + 64 * 32 + (NH2 - 1) * 64 * 64, 16, 64, tid, nthreads);
+    }
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// one level of the hash grid for one sample, F = 2: 8 gathers of 4 bytes, fp32 trilinear interpolation
+__device__ __forceinline__ void gather_level(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, float& f0, float& f1) {
+    const float s = m.scale[l];
+    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const uint32_t* lvl = table + m.offset[l];
+    uint32_t idx[8];
+    if ((m.hashed >> l) & 1u) {              // size is a power of two for hashed levels
+        const uint32_t mask = size - 1u;
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t h00 = hy0 ^ hz0, h10 = hy1 ^ hz0, h01 = hy0 ^ hz1, h11 = hy1 ^ hz1, gx1 = gx + 1u;
+        idx[0] = (gx ^ h00) & mask; idx[1] = (gx1 ^ h00) & mask; idx[2] = (gx ^ h10) & mask; idx[3] = (gx1 ^ h10) & mask;
+        idx[4] = (gx ^ h01) & mask; idx[5] = (gx1 ^ h01) & mask; idx[6] = (gx ^ h11) & mask; idx[7] = (gx1 ^ h11) & mask;
+    } else {                                  // dense: x + y*res + z*res^2 (mod size: only the x/y/z == res border can wrap, once)
+        const uint32_t r2 = res * res;
+        const uint32_t b00 = gx + gy * res + gz * r2;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t i = b00 + (c & 1) + ((c >> 1) & 1) * res + (c >> 2) * r2;
+            if (i >= size) i %= size;
+            idx[c] = i;
+        }
+    }
+    uint32_t v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(lvl + idx[c]);
+    const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+    f0 = 0.f; f1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {    // same weight expression and accumulation order as encode_level (grid_common.cuh)
+        const float w = ((c & 1) ? wx : ux) * (((c >> 1) & 1) ? wy : uy) * ((c >> 2) ? wz : uz);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[c]));
+        f0 = fmaf(w, f.x, f0); f1 = fmaf(w, f.y, f1);
+    }
+}
+
+__device__ __forceinline__ float act_out(float x, int act) {
+    if (act == MFN_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
+    if (act == MFN_ACT_EXP) return __expf(x);
+    return x;
+}
+
+// TMEM -> ReLU -> fp16 row of a [128 x 64] row-core tile (and optionally the same 16-byte chunks to a global blob tile)
+__device__ __forceinline__ void relu_epilogue64(uint32_t taddr, unsigned char* tile, unsigned char* gtile, int row) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 o;
+            o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
+            o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
+            o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
+            o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
+            const int off = tile_off(row, half * 32 + c * 8, 64);
+            *reinterpret_cast<uint4*>(tile + off) = o;
+            if (gtile) *reinterpret_cast<uint4*>(gtile + off) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ forward
+// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma)
+template <int NH2, int MODE>
+__global__ void __launch_bounds__(kFT, 4)
+field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
+    const int64_t n_tiles = (n + kFT - 1) / kFT;
+    stage_all_weights<NH2>(smem, a, tid, kFT, MODE != 2);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, kFwdCols);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t trow = tmem_addr(tbase, warp * 32, 0);   // this warp's lane quarter
+    const uint32_t sbase = smem_u32(smem);
+    uint32_t phase = 0;
+    const uint32_t* table = reinterpret_cast<const uint32_t*>(a.table);
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * kFT + tid;
+        const bool valid = i < n;
+        unsigned char* blob = (MODE == 1) ? a.blobs + (size_t)tile * kBlob : nullptr;
+        // ---- hash-grid gather -> X tile
+        float x = 0.5f, y = 0.5f, z = 0.5f;
+        if (valid) {
+            x = a.xyzs[3 * i]; y = a.xyzs[3 * i + 1]; z = a.xyzs[3 * i + 2];
+            x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
+            y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
+            z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {       // 4 levels = one 16-byte chunk of the row
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gather_level(table, m, 4 * c + j, x, y, z, f[2 * j], f[2 * j + 1]);
+                o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+            }
+            const int off = tile_off(tid, c * 8, 32);
+            *reinterpret_cast<uint4*>(smem + kFwdX + off) = o;
+            if (MODE == 1) *reinterpret_cast<uint4*>(blob + kBX + off) = o;
+        }
+        // ---- SH of the normalised direction -> CAT[:, 0:16]   (networks.py:145-146)
+        if (MODE != 2) {
+            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+            if (valid) {
+                const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float ux = (dx / nrm + 1.0f) / 2.0f, uy = (dy / nrm + 1.0f) / 2.0f, uz = (dz / nrm + 1.0f) / 2.0f;
+                float s[16];
+                sh4_eval(fmaf(ux, 2.f, -1.f), fmaf(uy, 2.f, -1.f), fmaf(uz, 2.f, -1.f), s);
+                o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
+                o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
+            }
+            const int off0 = tile_off(tid, 0, 32), off1 = tile_off(tid, 8, 32);
+            *reinterpret_cast<uint4*>(smem + kFwdC + off0) = o0;
+            *reinterpret_cast<uint4*>(smem + kFwdC + off1) = o1;
+            if (MODE == 1) { *reinterpret_cast<uint4*>(blob + kBC + off0) = o0; *reinterpret_cast<uint4*>(blob + kBC + off1) = o1; }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 1: H1 = relu(X . W1^T)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1u;
+        tc_fence_after();
+        relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH1 : nullptr, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- layer 2: h = H1 . W2^T (16 outputs, no activation); sigma = exp(h0)  (TruncExp forward)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 16, false, false);
+#pragma unroll
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1u;
+        tc_fence_after();
+        {
+            uint32_t r[16];
+            tmem_ld_x16(trow + kAccO, r);
+            tmem_ld_wait();
+            uint4 o0, o1;
+            o0.x = pack2(__uint_as_float(r[0]), __uint_as_float(r[1])); o0.y = pack2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            o0.z = pack2(__uint_as_float(r[4]), __uint_as_float(r[5])); o0.w = pack2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9])); o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
+            if (MODE != 2) {
+                const int off0 = tile_off(tid, 16, 32), off1 = tile_off(tid, 24, 32);
+                *reinterpret_cast<uint4*>(smem + kFwdC + off0) = o0;
+                *reinterpret_cast<uint4*>(smem + kFwdC + off1) = o1;
+                if (MODE == 1) { *reinterpret_cast<uint4*>(blob + kBC + off0) = o0; *reinterpret_cast<uint4*>(blob + kBC + off1) = o1; }
+            }
+        }
+        if (MODE == 2) { tc_fence_before(); __syncthreads(); continue; }   // (uniform) density only
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- rgb layer 1: H2 = relu(CAT . W3^T)
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1u;
+        tc_fence_after();
+        relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH2 : nullptr, tid);
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (NH2 == 2) {
+            // ---- rgb layer 2: H3 = relu(H2 . W4^T)
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+                for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
+                mma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1u;
+            tc_fence_after();
+            relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH3 : nullptr, tid);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+        // ---- rgb output layer: rgb = act(H . W5^T)[0:3], rounded to fp16 like tcnn's output
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 16, false, false);
+#pragma unroll
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1u;
+        tc_fence_after();
+        {
+            uint32_t r[8];
+            tmem_ld_x8(trow + kAccO, r);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float v = __half2float(__float2half_rn(act_out(__uint_as_float(r[k]), a.rgb_act)));
+                    a.rgbs[3 * i + k] = v;
+                    if (MODE == 1) a.rgbs_copy[3 * i + k] = v;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // TMEM and the tiles are free for the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, kFwdCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ backward
+// TMEM (fp32 dgrad accumulator) -> mask with relu'(activation tile row) -> fp16 dZ row written IN PLACE of the activation row
+__device__ __forceinline__ void mask_epilogue64(uint32_t taddr, unsigned char* tile, int row) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_x32(taddr + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4* p = reinterpret_cast<uint4*>(tile + tile_off(row, half * 32 + c * 8, 64));
+            const uint4 act = *p;
+            const __half2* ah = reinterpret_cast<const __half2*>(&act);
+            uint4 o;
+            uint32_t* ow = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 av = __half22float2(ah[k]);
+                ow[k] = pack2(av.x > 0.f ? __uint_as_float(r[8 * c + 2 * k]) : 0.f, av.y > 0.f ? __uint_as_float(r[8 * c + 2 * k + 1]) : 0.f);
+            }
+            *p = o;
+        }
+    }
+}
+
+template <int NH2>
+__global__ void __launch_bounds__(kFT, 2)
+field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_mma, bar_load;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
+    const int64_t n_tiles = (n + kFT - 1) / kFT;
+    stage_all_weights<NH2>(smem, a, tid, kFT, true);
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_load, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, kBwdCols);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t trow = tmem_addr(tbase, warp * 32, 0);
+    const uint32_t sbase = smem_u32(smem);
+    unsigned char* sBlob = smem + kBwdBlob;
+    const uint32_t sX = sbase + kBwdBlob + kBX, sH1 = sbase + kBwdBlob + kBH1, sC = sbase + kBwdBlob + kBC, sH2 = sbase + kBwdBlob + kBH2,
+                   sH3 = sbase + kBwdBlob + kBH3, sDZo = sbase + kBwdDZo;
+    const uint32_t sHL = (NH2 == 2) ? sH3 : sH2;                  // last hidden activation of the rgb net
+    unsigned char* pHL = sBlob + ((NH2 == 2) ? kBH3 : kBH2);
+    uint32_t ph_mma = 0, ph_load = 0;
+    uint32_t acc = 0;                                              // 0 on the CTA's first tile: weight-gradient MMAs overwrite
+    bool bad = false;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * kFT + tid;
+        const bool valid = i < n;
+        if (tid == 0) {   // the whole activation blob of this tile with one bulk async copy
+            mbar_arrive_expect_tx(&bar_load, NH2 == 2 ? kBlob : kBH3);
+            bulk_g2s(sBlob, a.blobs + (size_t)tile * kBlob, NH2 == 2 ? kBlob : kBH3, &bar_load);
+        }
+        // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
+        {
+            float g[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float yv = a.rgbs_copy[3 * i + k];
+                    float d = a.dL_drgbs[3 * i + k] * a.loss_scale;
+                    if (a.rgb_act == MFN_ACT_SIGMOID) d *= yv * (1.f - yv);
+                    else if (a.rgb_act == MFN_ACT_EXP) d *= yv;
+                    g[k] = d;
+                }
+            }
+            uint4 o0 = make_uint4(pack2(g[0], g[1]), pack2(g[2], 0.f), 0u, 0u);
+            const __half2* hh = reinterpret_cast<const __half2*>(&o0);
+            bad |= !isfinite(__low2float(hh[0])) || !isfinite(__high2float(hh[0])) || !isfinite(__low2float(hh[1]));
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 0, 16)) = o0;
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        mbar_wait(&bar_load, ph_load); ph_load ^= 1u;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- stage A: dH_last = dZ5 . W5 ;  dW5^T += H_last^T . dZ5
+        if (tid == 0) {
+            tc_fence_after();
+            mma_f16_ss(tbase + kAccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + kW5, 64, 0), idesc_f16(128, 64, false, true), 0u);
+            const uint32_t idw = idesc_f16(64, 16, true, true);
+#pragma unroll
+            for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW5, desc_mnmajor(sHL, 64, k0), desc_mnmajor(sDZo, 16, k0), idw, acc | (k0 > 0));
+            mma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        tc_fence_after();
+        mask_epilogue64(trow + kAccH, pHL, tid);                 // dZ of the last hidden layer, in place
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (NH2 == 2) {
+            // ---- stage B: dH2 = dZ4 . W4 ;  dW4^T += H2^T . dZ4
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_f16(128, 64, false, true);
+#pragma unroll
+                for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sH3, 64, k0), desc_mnmajor(sbase + kW4, 64, k0), id, k0 > 0);
+                const uint32_t idw = idesc_f16(64, 64, true, true);
+#pragma unroll
+                for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW4, desc_mnmajor(sH2, 64, k0), desc_mnmajor(sH3, 64, k0), idw, acc | (k0 > 0));
+                mma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            tc_fence_after();
+            mask_epilogue64(trow + kAccH, sBlob + kBH2, tid);    // dZ3 in place of H2
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+        // ---- stage C: dCAT = dZ3 . W3 (32 columns) ;  dW3 += dZ3^T . CAT
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 32, false, true);
+#pragma unroll
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sH2, 64, k0), desc_mnmajor(sbase + kW3, 32, k0), id, k0 > 0);
+            const uint32_t idw = idesc_f16(64, 32, true, true);
+#pragma unroll
+            for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW3, desc_mnmajor(sH2, 64, k0), desc_mnmajor(sC, 32, k0), idw, acc | (k0 > 0));
+            mma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        tc_fence_after();
+        {   // dh = dCAT[:, 16:32] ; dh[0] += loss_scale * dL/dsigma * exp(clamp(h0, -15, 15))   (TruncExp backward)
+            uint32_t r[16];
+            tmem_ld_x16(trow + kAccH + 16, r);
+            tmem_ld_wait();
+            float d0 = __uint_as_float(r[0]);
+            if (valid) {
+                const float h0 = __half2float(*reinterpret_cast<const __half*>(sBlob + kBC + tile_off(tid, 16, 32)));
+                d0 += a.dL_dsigmas[i] * expf(fminf(fmaxf(h0, -15.f), 15.f)) * a.loss_scale;
+            }
+            uint4 o0, o1;
+            o0.x = pack2(d0, __uint_as_float(r[1])); o0.y = pack2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            o0.z = pack2(__uint_as_float(r[4]), __uint_as_float(r[5])); o0.w = pack2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9])); o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            bad |= !isfinite(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 0, 16)) = o0;
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 8, 16)) = o1;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- stage D: dH1 = dZ2 . W2 ;  dW2^T += H1^T . dZ2
+        if (tid == 0) {
+            tc_fence_after();
+            mma_f16_ss(tbase + kAccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + kW2, 64, 0), idesc_f16(128, 64, false, true), 0u);
+            const uint32_t idw = idesc_f16(64, 16, true, true);
+#pragma unroll
+            for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW2, desc_mnmajor(sH1, 64, k0), desc_mnmajor(sDZo, 16, k0), idw, acc | (k0 > 0));
+            mma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        tc_fence_after();
+        mask_epilogue64(trow + kAccH, sBlob + kBH1, tid);        // dZ1 in place of H1
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- stage E: dX = dZ1 . W1 (32 columns) ;  dW1 += dZ1^T . X
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t id = idesc_f16(128, 32, false, true);
+#pragma unroll
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sH1, 64, k0), desc_mnmajor(sbase + kW1, 32, k0), id, k0 > 0);
+            const uint32_t idw = idesc_f16(64, 32, true, true);
+#pragma unroll
+            for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW1, desc_mnmajor(sH1, 64, k0), desc_mnmajor(sX, 32, k0), idw, acc | (k0 > 0));
+            mma_commit(&bar_mma);
+        }
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        tc_fence_after();
+        {   // dX row -> dfeats (n, 32) fp16
+            uint32_t r[32];
+            tmem_ld_x32(trow + kAccH, r);
+            tmem_ld_wait();
+            if (valid) {
+                uint4* dst = reinterpret_cast<uint4*>(a.dfeats + (size_t)i * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 o;
+                    o.x = pack2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])); o.y = pack2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                    o.z = pack2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])); o.w = pack2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                    dst[c] = o;
+                }
+            }
+        }
+        acc = 1u;
+        fence_async_smem();   // generic reads/writes of the tile area are ordered before the next bulk copy into it
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (bad && a.overflow) *a.overflow = 1;
+    // ---- flush this CTA's weight-gradient accumulators (M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16)
+    float* part = a.partials + (size_t)blockIdx.x * kNumWg;
+    if (acc == 0u) {
+        for (int q = tid; q < kNumWg; q += kFT) part[q] = 0.f;
+    } else {
+        tc_fence_after();
+        const int mrow = warp * 16 + (lane & 15);
+        const bool own = lane < 16;
+        constexpr int oW1 = 0, oW2 = 64 * 32, oW3 = oW2 + 16 * 64, oW4 = oW3 + 64 * 32, oW5 = oW4 + (NH2 - 1) * 64 * 64;
+        {
+            uint32_t r[32];
+            tmem_ld_x32(trow + kAccW1, r); tmem_ld_wait();          // dW1[out = m][in = j]
+            if (own) for (int j = 0; j < 32; ++j) part[oW1 + mrow * 32 + j] = __uint_as_float(r[j]);
+            tmem_ld_x32(trow + kAccW3, r); tmem_ld_wait();          // dW3[out = m][in = j]
+            if (own) for (int j = 0; j < 32; ++j) part[oW3 + mrow * 32 + j] = __uint_as_float(r[j]);
+            if (NH2 == 2) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                          // dW4^T[in = m][out = j]
+                    tmem_ld_x32(trow + kAccW4 + 32 * h, r); tmem_ld_wait();
+                    if (own) for (int j = 0; j < 32; ++j) part[oW4 + (32 * h + j) * 64 + mrow] = __uint_as_float(r[j]);
+                }
+            }
+        }
+        {
+            uint32_t r[16];
+            tmem_ld_x16(trow + kAccW2, r); tmem_ld_wait();          // dW2^T[in = m][out = j]
+            if (own) for (int j = 0; j < 16; ++j) part[oW2 + j * 64 + mrow] = __uint_as_float(r[j]);
+            tmem_ld_x16(trow + kAccW5, r); tmem_ld_wait();          // dW5^T[in = m][out = j]
+            if (own) for (int j = 0; j < 16; ++j) part[oW5 + j * 64 + mrow] = __uint_as_float(r[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, kBwdCols);
+}
+
+// d_params[j] += sum over CTAs of partials[c][j]; the first 3072 entries belong to the sigma net, the rest to the rgb net
+__global__ void reduce_wgrad_kernel(const float* __restrict__ partials, int n_parts, int n_rgb, float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 3072 + n_rgb) return;
+    float s = 0.f;
+    for (int c = 0; c < n_parts; ++c) s += partials[(size_t)c * kNumWg + j];
+    if (j < 3072) d_sigma[j] += s; else d_rgb[j - 3072] += s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------ host side
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms = v > 0 ? v : kNumSMs;
+    }
+    return g_num_sms;
+}
+
+bool fused_field_supported(const mfn_field_cfg* c) {
+    return c->grid.n_levels == 16 && c->grid.n_features == 2 && c->sigma_width == 64 && c->sigma_hidden == 1 && c->rgb_width == 64 &&
+           (c->rgb_hidden == 1 || c->rgb_hidden == 2);
+}
+int fused_bwd_max_ctas() { return 2 * num_sms(); }
+size_t fused_blob_bytes(int64_t n_max) { return (size_t)ceil_div(n_max, kFT) * kBlob; }
+size_t fused_partial_bytes() { return (size_t)fused_bwd_max_ctas() * kNumWg * sizeof(float); }
+
+template <int NH2, int MODE>
+static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
+    static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), true);
+    (void)once;
+    const int64_t tiles = ceil_div(a.n_max, kFT);
+    const int64_t cap = 4 * (int64_t)num_sms();
+    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFT, kFwdSmem, st>>>(a, m);
+}
+
+// mode: 0 inference, 1 training, 2 density only
+int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st) {
+    ProfScope ps(mode == 2 ? "density_fwd" : "field_fwd", st);
+    if (rgb_hidden == 2) { if (mode == 0) launch_fwd<2, 0>(a, m, st); else if (mode == 1) launch_fwd<2, 1>(a, m, st); else launch_fwd<2, 2>(a, m, st); }
+    else { if (mode == 0) launch_fwd<1, 0>(a, m, st); else if (mode == 1) launch_fwd<1, 1>(a, m, st); else launch_fwd<1, 2>(a, m, st); }
+    return check_launch("mfn_field_fwd(fused)", st);
+}
+
+template <int NH2>
+static int launch_bwd(const FusedArgs& a, cudaStream_t st) {
+    static bool once = (cudaFuncSetAttribute(field_bwd_fused_kernel<NH2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), true);
+    (void)once;
+    const int64_t tiles = ceil_div(a.n_max, kFT);
+    const int64_t cap = fused_bwd_max_ctas();
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
+    field_bwd_fused_kernel<NH2><<<grid, kFT, kBwdSmem, st>>>(a);
+    return (int)grid;
+}
+
+int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, cudaStream_t st) {
+    int grid;
+    {
+        ProfScope ps("field_bwd", st);
+        grid = rgb_hidden == 2 ? launch_bwd<2>(a, st) : launch_bwd<1>(a, st);
+    }
+    int rc = check_launch("mfn_field_bwd(fused)", st);
+    if (rc != MFN_OK) return rc;
+    const int n_rgb = 64 * 32 + (rgb_hidden - 1) * 64 * 64 + 16 * 64;
+    {
+        ProfScope ps("reduce_wgrad", st);
+        reduce_wgrad_kernel<<<(3072 + n_rgb + 127) / 128, 128, 0, st>>>(a.partials, grid, n_rgb, d_sigma_params, d_rgb_params);
+    }
+    return check_launch("mfn_field_bwd(reduce)", st);
+}
+
+}  // namespace mfn

@@ -47,4 +47,28 @@ struct EncArgs {
 int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m, int F, __half* out, cudaStream_t st);
 int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F, float* dgrid, int32_t* overflow_flag, cudaStream_t st);
 
+// ---- fused tcgen05 field kernels (field_fused.cu) ----
+struct FusedArgs {
+    const float* xyzs; const float* dirs;
+    float mn[3], mx[3];
+    int64_t n_max; const int32_t* n_dev;
+    const __half* table;
+    const __half* w_sigma;   // [W1 64x32][W2 16x64]
+    const __half* w_rgb;     // [W3 64x32]([W4 64x64])[W5 16x64]
+    float* sigmas; float* rgbs;
+    float* rgbs_copy;        // training: second copy of rgbs kept in the workspace for the backward pass
+    unsigned char* blobs;    // training: activation tiles, 64 KiB per 128 samples
+    int rgb_act;
+    // backward only
+    const float* dL_dsigmas; const float* dL_drgbs; float loss_scale;
+    __half* dfeats;          // (n, 32) fp16 row-major, loss-scaled
+    float* partials;         // [gridDim.x][10240] per-CTA weight gradients
+    int32_t* overflow;
+};
+bool fused_field_supported(const mfn_field_cfg* c);
+size_t fused_blob_bytes(int64_t n_max);
+size_t fused_partial_bytes();
+int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st);   // mode 0 inference, 1 training, 2 density
+int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, cudaStream_t st);
+
 }  // namespace mfn
