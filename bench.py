@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()

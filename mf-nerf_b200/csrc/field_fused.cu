@@ -74,15 +74,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// one level of the hash grid for one sample, F = 2: 8 gathers of 4 bytes, fp32 trilinear interpolation
-__device__ __forceinline__ void gather_level(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, float& f0, float& f1) {
+// one level of the hash grid for one sample, F = 2: 8 gathers of 4 bytes, fp32 trilinear interpolation -> packed half2
+__device__ __forceinline__ uint32_t gather_level(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z) {
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = px - fx, wy = py - fy, wz = pz - fz;
     const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-    const uint32_t* lvl = table + m.offset[l];
+    const uint32_t* lvl = table + off;
     uint32_t idx[8];
     if ((m.hashed >> l) & 1u) {              // size is a power of two for hashed levels
         const uint32_t mask = size - 1u;
@@ -90,13 +90,14 @@ __device__ __forceinline__ void gather_level(const uint32_t* __restrict__ table,
         const uint32_t h00 = hy0 ^ hz0, h10 = hy1 ^ hz0, h01 = hy0 ^ hz1, h11 = hy1 ^ hz1, gx1 = gx + 1u;
         idx[0] = (gx ^ h00) & mask; idx[1] = (gx1 ^ h00) & mask; idx[2] = (gx ^ h10) & mask; idx[3] = (gx1 ^ h10) & mask;
         idx[4] = (gx ^ h01) & mask; idx[5] = (gx1 ^ h01) & mask; idx[6] = (gx ^ h11) & mask; idx[7] = (gx1 ^ h11) & mask;
-    } else {                                  // dense: x + y*res + z*res^2 (mod size: only the x/y/z == res border can wrap, once)
+    } else {                                  // dense: x + y*res + z*res^2, mod size (only a corner on the x/y/z == res border wraps)
         const uint32_t r2 = res * res;
         const uint32_t b00 = gx + gy * res + gz * r2;
+        const bool wrap = b00 + 1u + res + r2 >= size;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             uint32_t i = b00 + (c & 1) + ((c >> 1) & 1) * res + (c >> 2) * r2;
-            if (i >= size) i %= size;
+            if (wrap) i %= size;
             idx[c] = i;
         }
     }
@@ -104,13 +105,14 @@ __device__ __forceinline__ void gather_level(const uint32_t* __restrict__ table,
 #pragma unroll
     for (int c = 0; c < 8; ++c) v[c] = __ldg(lvl + idx[c]);
     const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
-    f0 = 0.f; f1 = 0.f;
+    float f0 = 0.f, f1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {    // same weight expression and accumulation order as encode_level (grid_common.cuh)
         const float w = ((c & 1) ? wx : ux) * (((c >> 1) & 1) ? wy : uy) * ((c >> 2) ? wz : uz);
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[c]));
         f0 = fmaf(w, f.x, f0); f1 = fmaf(w, f.y, f1);
     }
+    return pack2(f0, f1);
 }
 
 __device__ __forceinline__ float act_out(float x, int act) {
@@ -119,39 +121,40 @@ __device__ __forceinline__ float act_out(float x, int act) {
     return x;
 }
 
-// TMEM -> ReLU -> fp16 row of a [128 x 64] row-core tile (and optionally the same 16-byte chunks to a global blob tile)
-__device__ __forceinline__ void relu_epilogue64(uint32_t taddr, unsigned char* tile, unsigned char* gtile, int row) {
+// TMEM (32 fp32 columns starting at col0) -> ReLU -> fp16 -> columns col0..col0+31 of row `row` of a [128 x 64] row-core tile
+__device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* tile, int row, int col0) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr + col0, r);
+    tmem_ld_wait();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld_x32(taddr + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint4 o;
-            o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
-            o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
-            o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
-            o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
-            const int off = tile_off(row, half * 32 + c * 8, 64);
-            *reinterpret_cast<uint4*>(tile + off) = o;
-            if (gtile) *reinterpret_cast<uint4*>(gtile + off) = o;
-        }
+    for (int c = 0; c < 4; ++c) {
+        uint4 o;
+        o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
+        o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
+        o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
+        o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
+        *reinterpret_cast<uint4*>(tile + tile_off(row, col0 + c * 8, 64)) = o;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------ forward
-// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma)
+// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma).
+// 256 threads: thread t works on sample row t % 128 (= its TMEM lane); the two threads of a row split the 16 grid levels in the
+// gather phase and the 64 accumulator columns in the hidden-layer epilogues.  In training mode every published tile is also sent
+// to the blob with one bulk async store (shared -> global) issued by thread 0.
+constexpr int kFwdThreads = 256;
+
 template <int NH2, int MODE>
-__global__ void __launch_bounds__(kFT, 4)
+__global__ void __launch_bounds__(kFwdThreads, 4)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kFT - 1), hsel = tid >> 7;
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
-    stage_all_weights<NH2>(smem, a, tid, kFT, MODE != 2);
+    stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE != 2);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, kFwdCols);
     fence_async_smem();
@@ -159,38 +162,33 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base_s;
-    const uint32_t trow = tmem_addr(tbase, warp * 32, 0);   // this warp's lane quarter
+    const uint32_t trow = tmem_addr(tbase, (warp & 3) * 32, 0);   // this warp's lane quarter
     const uint32_t sbase = smem_u32(smem);
     uint32_t phase = 0;
     const uint32_t* table = reinterpret_cast<const uint32_t*>(a.table);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kFT + tid;
+        const int64_t i = tile * kFT + row;
         const bool valid = i < n;
         unsigned char* blob = (MODE == 1) ? a.blobs + (size_t)tile * kBlob : nullptr;
-        // ---- hash-grid gather -> X tile
-        float x = 0.5f, y = 0.5f, z = 0.5f;
-        if (valid) {
-            x = a.xyzs[3 * i]; y = a.xyzs[3 * i + 1]; z = a.xyzs[3 * i + 2];
-            x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
-            y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
-            z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {       // 4 levels = one 16-byte chunk of the row
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        // ---- hash-grid gather -> X tile (levels 8*hsel .. 8*hsel+7 of this thread's row)
+        {
+            float x = 0.5f, y = 0.5f, z = 0.5f;
             if (valid) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gather_level(table, m, 4 * c + j, x, y, z, f[2 * j], f[2 * j + 1]);
-                o.x = pack2(f[0], f[1]); o.y = pack2(f[2], f[3]); o.z = pack2(f[4], f[5]); o.w = pack2(f[6], f[7]);
+                x = a.xyzs[3 * i]; y = a.xyzs[3 * i + 1]; z = a.xyzs[3 * i + 2];
+                x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
+                y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
+                z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
             }
-            const int off = tile_off(tid, c * 8, 32);
-            *reinterpret_cast<uint4*>(smem + kFwdX + off) = o;
-            if (MODE == 1) *reinterpret_cast<uint4*>(blob + kBX + off) = o;
+#pragma unroll 2
+            for (int j = 0; j < 8; ++j) {
+                const int l = 8 * hsel + j;
+                const uint32_t v = valid ? gather_level(table, m, l, x, y, z) : 0u;
+                *reinterpret_cast<uint32_t*>(smem + kFwdX + tile_off(row, 2 * l, 32)) = v;
+            }
         }
         // ---- SH of the normalised direction -> CAT[:, 0:16]   (networks.py:145-146)
-        if (MODE != 2) {
+        if (MODE != 2 && hsel == 0) {
             uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
             if (valid) {
                 const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
@@ -201,10 +199,8 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
                 o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
             }
-            const int off0 = tile_off(tid, 0, 32), off1 = tile_off(tid, 8, 32);
-            *reinterpret_cast<uint4*>(smem + kFwdC + off0) = o0;
-            *reinterpret_cast<uint4*>(smem + kFwdC + off1) = o1;
-            if (MODE == 1) { *reinterpret_cast<uint4*>(blob + kBC + off0) = o0; *reinterpret_cast<uint4*>(blob + kBC + off1) = o1; }
+            *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 0, 32)) = o0;
+            *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 8, 32)) = o1;
         }
         fence_async_smem();
         tc_fence_before();
@@ -215,11 +211,12 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g(blob + kBX, smem + kFwdX, kFT * 32 * 2); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
         tc_fence_after();
-        relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH1 : nullptr, tid);
+        relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -229,11 +226,12 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g(blob + kBH1, smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
-        mbar_wait(&bar, phase); phase ^= 1u;
-        tc_fence_after();
-        {
+        if (hsel == 0) {
+            mbar_wait(&bar, phase);
+            tc_fence_after();
             uint32_t r[16];
             tmem_ld_x16(trow + kAccO, r);
             tmem_ld_wait();
@@ -244,27 +242,27 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
             if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
             if (MODE != 2) {
-                const int off0 = tile_off(tid, 16, 32), off1 = tile_off(tid, 24, 32);
-                *reinterpret_cast<uint4*>(smem + kFwdC + off0) = o0;
-                *reinterpret_cast<uint4*>(smem + kFwdC + off1) = o1;
-                if (MODE == 1) { *reinterpret_cast<uint4*>(blob + kBC + off0) = o0; *reinterpret_cast<uint4*>(blob + kBC + off1) = o1; }
+                *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 16, 32)) = o0;
+                *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 24, 32)) = o1;
             }
         }
-        if (MODE == 2) { tc_fence_before(); __syncthreads(); continue; }   // (uniform) density only
+        phase ^= 1u;
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (MODE == 2) continue;   // (uniform) density only
         // ---- rgb layer 1: H2 = relu(CAT . W3^T)
         if (tid == 0) {
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g(blob + kBC, smem + kFwdC, kFT * 32 * 2); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
         tc_fence_after();
-        relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH2 : nullptr, tid);
+        relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -275,11 +273,12 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
                 for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
+                if (MODE == 1) { bulk_s2g(blob + kBH2, smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
                 mma_commit(&bar);
             }
             mbar_wait(&bar, phase); phase ^= 1u;
             tc_fence_after();
-            relu_epilogue64(trow + kAccH, smem + kFwdH, MODE == 1 ? blob + kBH3 : nullptr, tid);
+            relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -290,11 +289,12 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
-        mbar_wait(&bar, phase); phase ^= 1u;
-        tc_fence_after();
-        {
+        if (hsel == 0) {
+            mbar_wait(&bar, phase);
+            tc_fence_after();
             uint32_t r[8];
             tmem_ld_x8(trow + kAccO, r);
             tmem_ld_wait();
@@ -307,9 +307,11 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 }
             }
         }
+        phase ^= 1u;
         tc_fence_before();
         __syncthreads();   // TMEM and the tiles are free for the next tile
     }
+    if (MODE == 1 && tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, kFwdCols);
@@ -586,7 +588,7 @@ static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
     const int64_t cap = 4 * (int64_t)num_sms();
-    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFT, kFwdSmem, st>>>(a, m);
+    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, kFwdSmem, st>>>(a, m);
 }
 
 // mode: 0 inference, 1 training, 2 density only

@@ -1,0 +1,61 @@
+"""Host-side logic of the data-parallel path: one process per GPU, rays sharded across ranks, ONE
+all-reduce of the flat gradient per training step, image row tiles at test time (no collective).
+
+Nothing here touches CUDA directly, so the same code runs under `gloo` on CPU tensors (tests/test_multi_cpu.py) and under
+`nccl` on the GPUs (engine.py, bench.py)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    """(rank, local_rank, world_size) from the torchrun environment; (0, 0, 1) when launched plainly"""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_seed(base_seed, rank):
+    """every rank samples its OWN rays (the reference's per-rank dataloader sampling, datasets/base.py:22-44)"""
+    return int(base_seed) + 1000003 * int(rank)
+
+
+def model_seed(base_seed):
+    """...but the SAME initial parameters and the same density-grid cell sampling on every rank, so the replicas stay identical"""
+    return int(base_seed)
+
+
+def allreduce_gradients(flat_grads, world_size, group=None):
+    """sum the flat gradient [xyz_encoder.params | rgb_net.params] over ranks, in place.  The division by world_size (DDP's
+    gradient averaging, train.py uses Lightning DDP) is folded into the optimiser's grad_scale -- see grad_scale()."""
+    if world_size > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads
+
+
+def grad_scale(loss_scale, world_size):
+    """factor the fused Adam applies to the summed, loss-scaled gradient"""
+    return 1.0 / (float(loss_scale) * int(world_size))
+
+
+def tile_rows(height, rank, world_size):
+    """[row0, row1) of the image rows rendered by `rank` (contiguous row tiles; remainder rows go to the first ranks)"""
+    base, rem = divmod(int(height), int(world_size))
+    row0 = rank * base + min(rank, rem)
+    return row0, row0 + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value, device, world_size, group=None):
+    """max of a python float over ranks (bench.py: the step time of a job is its slowest rank's)"""
+    if world_size == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device, world_size, group=None):
+    if world_size == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())

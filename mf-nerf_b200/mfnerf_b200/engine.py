@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib, field_ops
+from . import dist as mdist
 from ._lib import call, ptr, stream_ptr
 
 MAX_SAMPLES = 1024          # rendering.py:7
@@ -245,7 +246,7 @@ class NGPEngine:
     def _optimizer_step(self, lr=None):
         self.step_count += 1
         call("mfn_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
-             float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, 1.0 / (self.loss_scale * self.world_size), ptr(self.overflow), 1,
+             float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 1,
              stream_ptr(self.dev))
 
     def capture(self):
@@ -275,8 +276,7 @@ class NGPEngine:
         if rays_o is not None:
             self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
         self._run_forward_backward()
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+        mdist.allreduce_gradients(self.grads, self.world_size, self.pg)
         self._optimizer_step(lr)
 
     def _run_forward_backward(self):
@@ -295,8 +295,7 @@ class NGPEngine:
             self.update_density_grid(warmup=global_step < 256)
         self.rays.copy_(batch, non_blocking=True)
         self._run_forward_backward()
-        if self.world_size > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+        mdist.allreduce_gradients(self.grads, self.world_size, self.pg)
         self._optimizer_step(lr)
 
     def snapshot(self):
