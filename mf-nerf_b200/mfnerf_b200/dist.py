@@ -24,11 +24,15 @@ def model_seed(base_seed):
     return int(base_seed)
 
 
-def allreduce_gradients(flat_grads, world_size, group=None):
+def allreduce_gradients(flat_grads, world_size, group=None, overflow_flag=None):
     """sum the flat gradient [xyz_encoder.params | rgb_net.params] over ranks, in place.  The division by world_size (DDP's
-    gradient averaging, train.py uses Lightning DDP) is folded into the optimiser's grad_scale -- see grad_scale()."""
+    gradient averaging, train.py uses Lightning DDP) is folded into the optimiser's grad_scale -- see grad_scale().
+    `overflow_flag` (int32 tensor, 1 = an fp16 gradient overflowed on this rank) is max-reduced so that every replica takes
+    the same skip-or-step decision (GradScaler semantics under DDP)."""
     if world_size > 1:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+        if overflow_flag is not None:
+            dist.all_reduce(overflow_flag, op=dist.ReduceOp.MAX, group=group)
     return flat_grads
 
 

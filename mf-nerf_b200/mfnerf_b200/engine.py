@@ -276,7 +276,7 @@ class NGPEngine:
         if rays_o is not None:
             self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
         self._run_forward_backward()
-        mdist.allreduce_gradients(self.grads, self.world_size, self.pg)
+        mdist.allreduce_gradients(self.grads, self.world_size, self.pg, self.overflow)
         self._optimizer_step(lr)
 
     def _run_forward_backward(self):
@@ -295,7 +295,7 @@ class NGPEngine:
             self.update_density_grid(warmup=global_step < 256)
         self.rays.copy_(batch, non_blocking=True)
         self._run_forward_backward()
-        mdist.allreduce_gradients(self.grads, self.world_size, self.pg)
+        mdist.allreduce_gradients(self.grads, self.world_size, self.pg, self.overflow)
         self._optimizer_step(lr)
 
     def snapshot(self):
