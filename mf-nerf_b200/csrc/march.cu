@@ -9,18 +9,66 @@
 // Algorithmic bytes: 60 B/ray + 32 B/sample (+ 8 B/sample stash write+read, + C*G^3/8 B of bitfield).
 #include "march.cuh"
 #include "../../include/mfnerf_b200.h"
+#include <stdlib.h>
 
 namespace mfn {
 
-constexpr int kMarchWarpsPerCta = 8;
+constexpr int kMarchWarpsPerCta = 8;     // march_write: one warp per ray
+constexpr int kCountThreads = 128;
+constexpr int kWsHeader = 256;           // workspace: [header: ray queue counter][counts][stash]
 
-__global__ void __launch_bounds__(kMarchWarpsPerCta * 32)
+// Persistent groups with a dynamic ray queue: group g starts on ray g, and whenever its ray is finished it takes the next
+// unclaimed ray (one atomicAdd per ray).  A warp therefore never idles on its longest ray, which halves the number of batches
+// on the Lego-shaped workload (ray lengths vary 10x).  *queue must be 0 at launch (memset node in front of the kernel).
+template <int kMarchLanes, bool ONE_CASCADE, bool CONST_DT>
+__global__ void __launch_bounds__(kCountThreads)
 march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
                    const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
                    const float* __restrict__ noise, int max_samples, int64_t n_rays,
-                   int32_t* __restrict__ counts, float2* __restrict__ stash) {
+                   int32_t* __restrict__ counts, float2* __restrict__ stash, unsigned int* __restrict__ queue) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int kCountGroupsPerCta = kCountThreads / kMarchLanes;
+    const int lane = threadIdx.x & 31, sub = lane & (kMarchLanes - 1), gbase = lane & ~(kMarchLanes - 1);
+    const int64_t n_groups = (int64_t)gridDim.x * kCountGroupsPerCta;
+    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
+    GroupState g;
+    g.alive = false; g.n = 0; g.t_base = 0.f; g.t2 = 0.f; g.pending = -INFINITY;
+    int64_t r = (int64_t)blockIdx.x * kCountGroupsPerCta + (threadIdx.x / kMarchLanes);   // first ray of this group
+    bool have = false;        // group-uniform: r is a ray in progress
+    bool exhausted = false;   // group-uniform: the queue has run dry
+    float2* my = stash;
+    while (true) {
+        if (!have && !exhausted) {     // pick up a ray (the first one is pre-assigned)
+            if (r >= n_rays) exhausted = true;
+            else {
+                const RayConst q = make_ray(rays_o, rays_d, r);
+                float t1 = hits_t[2 * r];
+                const float t2 = hits_t[2 * r + 1];
+                if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);  // only the first sample is jittered (l.195-198)
+                group_begin(g, q, t1, t2, max_samples);
+                my = stash + r * (int64_t)max_samples;
+                have = true;
+            }
+        }
+        if (!__any_sync(FULL, have)) break;
+        group_step<kMarchLanes, ONE_CASCADE, CONST_DT>(g, max_samples, c, bitfield, lane,
+                                                       [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); });
+        const bool done = have && !g.alive;   // ray done: publish its count and claim the next one
+        unsigned int nxt = 0;
+        if (done && sub == 0) { counts[r] = g.n; nxt = atomicAdd(queue, 1u); }
+        nxt = __shfl_sync(FULL, nxt, gbase);
+        if (done) { r = n_groups + (int64_t)nxt; have = false; }
+    }
+}
+
+// one warp per ray (MFN_MARCH_K=32, the default)
+template <bool ONE_CASCADE, bool CONST_DT>
+__global__ void __launch_bounds__(kCountThreads)
+march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+                        const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
+                        const float* __restrict__ noise, int max_samples, int64_t n_rays, int32_t* __restrict__ counts, float2* __restrict__ stash) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * kMarchWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t r = (int64_t)blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5);
     if (r >= n_rays) return;
     const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
     const RayConst q = make_ray(rays_o, rays_d, r);
@@ -28,10 +76,31 @@ march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ r
     const float t2 = hits_t[2 * r + 1];
     if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);  // only the first sample is jittered (l.195-198)
     float2* my = stash + r * (int64_t)max_samples;
-    float t_after;
-    const int n = march_ray_warp(t1, t2, max_samples, q, c, bitfield, lane,
-                                 [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); }, &t_after);
+    const int n = march_ray_warp<ONE_CASCADE, CONST_DT>(t1, t2, max_samples, q, c, bitfield, lane,
+                                                        [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); });
     if (lane == 0) counts[r] = n;
+}
+
+// thread-per-ray variant (the reference's control flow): far fewer instructions (the DDA skip probes ~1/3 of the lattice points)
+// but one long dependent chain per ray; MFN_MARCH_K=1 selects it, LPW = active lanes per warp
+template <int LPW>
+__global__ void __launch_bounds__(32)
+march_count_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
+                          const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
+                          const float* __restrict__ noise, int max_samples, int64_t n_rays, int32_t* __restrict__ counts, float2* __restrict__ stash) {
+    if (threadIdx.x >= LPW) return;
+    const int64_t r = (int64_t)blockIdx.x * LPW + threadIdx.x;
+    if (r >= n_rays) return;
+    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
+    const RayConst q = make_ray(rays_o, rays_d, r);
+    float t1 = hits_t[2 * r];
+    const float t2 = hits_t[2 * r + 1];
+    if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);
+    float2* my = stash + r * (int64_t)max_samples;
+    float t_after;
+    int n = 0;
+    if (t1 >= 0.0f) n = march_ray_thread(t1, t2, max_samples, q, c, bitfield, [&](int k, float tk, float dt, float, float, float) { my[k] = make_float2(tk, dt); }, &t_after);
+    counts[r] = n;
 }
 
 constexpr int kScanThreads = 1024;
@@ -97,6 +166,51 @@ march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ r
     }
 }
 
+// scan + write in one kernel (mfn_raymarching_train): every CTA first sums the counts of all rays in front of its own 8 rays
+// (<= 32 KiB of L2-resident int32 per CTA, read with 16-byte loads), which replaces the single-CTA prefix-sum kernel and its
+// launch; then writes rays_a and expands the stash exactly like march_write_kernel.  The CTA owning the last ray publishes the
+// total in counter[0].
+__global__ void __launch_bounds__(kMarchWarpsPerCta * 32)
+march_scan_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const int32_t* __restrict__ counts,
+                        const float2* __restrict__ stash, int max_samples, int64_t n_rays, int64_t capacity, int64_t* __restrict__ rays_a,
+                        int32_t* __restrict__ counter, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                        float* __restrict__ ts) {
+    __shared__ long long warp_sum[kMarchWarpsPerCta];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t first = (int64_t)blockIdx.x * kMarchWarpsPerCta;        // first ray of this CTA (a multiple of 8 -> 16-byte aligned counts)
+    long long acc = 0;
+    const int4* c4 = reinterpret_cast<const int4*>(counts);
+    for (int64_t i = tid; i < first / 4; i += kMarchWarpsPerCta * 32) { const int4 v = __ldg(c4 + i); acc += (long long)v.x + v.y + v.z + v.w; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) warp_sum[warp] = acc;
+    __syncthreads();
+    long long start = 0;
+#pragma unroll
+    for (int w = 0; w < kMarchWarpsPerCta; ++w) start += warp_sum[w];
+    const int64_t r = first + warp;
+    for (int w = 0; w < warp; ++w) start += (first + w < n_rays) ? counts[first + w] : 0;
+    if (r >= n_rays) return;
+    const int n = counts[r];
+    if (lane == 0) {
+        int64_t* row = rays_a + 3 * r;
+        row[0] = r; row[1] = start; row[2] = n;
+        if (r == n_rays - 1) { counter[0] = (int32_t)(start + n); counter[1] = (int32_t)n_rays; }
+    }
+    if (n == 0) return;
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float2* my = stash + r * (int64_t)max_samples;
+    for (int s = lane; s < n; s += 32) {
+        const int64_t o = start + s;
+        if (o >= capacity) break;
+        const float2 td = my[s];
+        xyzs[3 * o] = __fmaf_rn(dx, td.x, ox); xyzs[3 * o + 1] = __fmaf_rn(dy, td.x, oy); xyzs[3 * o + 2] = __fmaf_rn(dz, td.x, oz);
+        dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+        ts[o] = td.x; deltas[o] = td.y;
+    }
+}
+
 // test-time marcher: one thread per alive ray, sequential control flow of the reference; writes the zero
 // padding itself so the caller needs no memset.  (ref: raymarching.cu:353-403)
 __global__ void march_test_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t,
@@ -136,9 +250,9 @@ using namespace mfn;
 
 extern "C" int64_t mfn_march_train_workspace_bytes(int64_t n_rays, int max_samples) {
     if (n_rays < 0 || max_samples < 1) return -1;
-    // [counts: n_rays int32, padded to 256 B][stash: n_rays * max_samples float2]
+    // [header 256 B: ray queue][counts: n_rays int32, padded to 256 B][stash: n_rays * max_samples float2]
     const int64_t counts = ((n_rays * 4 + 255) / 256) * 256;
-    return counts + n_rays * (int64_t)max_samples * 8;
+    return kWsHeader + counts + n_rays * (int64_t)max_samples * 8;
 }
 
 static bool march_args_ok(int cascades, int grid_size, int max_samples, const char* name) {
@@ -149,28 +263,69 @@ static bool march_args_ok(int cascades, int grid_size, int max_samples, const ch
     return true;
 }
 
-extern "C" int mfn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
-                                     int cascades, float scale, float exp_step_factor, const float* noise, int grid_size,
-                                     int max_samples, int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
+static int march_count_impl(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                            int cascades, float scale, float exp_step_factor, const float* noise, int grid_size,
+                            int max_samples, int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
+                            int64_t workspace_bytes, void* stream, bool with_scan) {
     if (!march_args_ok(cascades, grid_size, max_samples, "mfn_march_train_count")) return MFN_ERR_ARG;
     if (n_rays < 0 || !counter) { set_error("mfn_march_train_count: bad argument"); return MFN_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n_rays == 0) { cudaMemsetAsync(counter, 0, 8, st); return check_launch("mfn_march_train_count", st); }
     if (!rays_o || !rays_d || !hits_t || !bitfield || !noise || !rays_a || !workspace) { set_error("mfn_march_train_count: null pointer"); return MFN_ERR_ARG; }
     if (workspace_bytes < mfn_march_train_workspace_bytes(n_rays, max_samples)) { set_error("mfn_march_train_count: workspace too small"); return MFN_ERR_ARG; }
-    int32_t* counts = (int32_t*)workspace;
-    float2* stash = (float2*)((char*)workspace + ((n_rays * 4 + 255) / 256) * 256);
-    const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
+    unsigned int* queue = (unsigned int*)workspace;
+    int32_t* counts = (int32_t*)((char*)workspace + kWsHeader);
+    float2* stash = (float2*)((char*)workspace + kWsHeader + ((n_rays * 4 + 255) / 256) * 256);
+    // lanes per ray and rays per group are tunables (MFN_MARCH_K, MFN_MARCH_RPG); see DESIGN.md for the measured choice
+    static float rays_per_group = 0.f;
+    static int K = 0;
+    if (K == 0) {
+        const char* e = getenv("MFN_MARCH_RPG"); rays_per_group = e ? (float)atof(e) : 1.0f; if (!(rays_per_group >= 1.f)) rays_per_group = 1.f;
+        e = getenv("MFN_MARCH_K"); K = e ? atoi(e) : 32; if (K != 1 && K != 4 && K != 8 && K != 16 && K != 32) K = 32;
+    }
+    const int groups_per_cta = kCountThreads / (K > 1 ? K : 8);
+    int64_t blocks = (int64_t)((double)n_rays / (groups_per_cta * (double)rays_per_group) + 0.999);
+    const int64_t cap = (int64_t)kNumSMs * 14;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
     {
         ProfScope ps("march_count", st);
-        march_count_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale,
-                                                                      exp_step_factor, noise, max_samples, n_rays, counts, stash);
+        cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);
+#define MFN_MC(KK, A, B) march_count_kernel<KK, A, B><<<(unsigned)blocks, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, \
+                                                                                  exp_step_factor, noise, max_samples, n_rays, counts, stash, queue)
+#define MFN_MCK(KK) { if (one && cdt) MFN_MC(KK, true, true); else if (one) MFN_MC(KK, true, false); else if (cdt) MFN_MC(KK, false, true); else MFN_MC(KK, false, false); }
+        const bool one = cascades == 1, cdt = exp_step_factor == 0.0f;
+        if (K == 1) {
+            static int lpw = 0;
+            if (lpw == 0) { const char* e2 = getenv("MFN_MARCH_LPW"); lpw = e2 ? atoi(e2) : 32; }
+            if (lpw == 8) march_count_thread_kernel<8><<<(unsigned)ceil_div(n_rays, 8), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
+            else if (lpw == 16) march_count_thread_kernel<16><<<(unsigned)ceil_div(n_rays, 16), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
+            else march_count_thread_kernel<32><<<(unsigned)ceil_div(n_rays, 32), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
+        } else if (K == 4) MFN_MCK(4) else if (K == 8) MFN_MCK(8) else if (K == 16) MFN_MCK(16)
+        else {
+            const unsigned wb = (unsigned)ceil_div(n_rays, kCountThreads / 32);
+#define MFN_MW(A, B) march_count_warp_kernel<A, B><<<wb, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, \
+                                                                                noise, max_samples, n_rays, counts, stash)
+            if (one && cdt) MFN_MW(true, true); else if (one) MFN_MW(true, false); else if (cdt) MFN_MW(false, true); else MFN_MW(false, false);
+#undef MFN_MW
+        }
+#undef MFN_MCK
+#undef MFN_MC
     }
-    note_launch(1);
-    { ProfScope ps("march_scan", st);
-      scan_rays_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, rays_a, counter); }
+    if (with_scan) {
+        note_launch(1);
+        ProfScope ps("march_scan", st);
+        scan_rays_kernel<<<1, kScanThreads, 0, st>>>(counts, n_rays, rays_a, counter);
+    }
     return check_launch("mfn_march_train_count", st);
+}
+
+extern "C" int mfn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* bitfield,
+                                     int cascades, float scale, float exp_step_factor, const float* noise, int grid_size,
+                                     int max_samples, int64_t n_rays, int64_t* rays_a, int32_t* counter, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+    return march_count_impl(rays_o, rays_d, hits_t, bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples, n_rays, rays_a, counter,
+                            workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int mfn_march_train_write(const float* rays_o, const float* rays_d, const int64_t* rays_a, const void* workspace,
@@ -179,7 +334,7 @@ extern "C" int mfn_march_train_write(const float* rays_o, const float* rays_d, c
     if (n_rays < 0 || capacity < 0 || max_samples < 1) { set_error("mfn_march_train_write: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0 || capacity == 0) return MFN_OK;
     if (!rays_o || !rays_d || !rays_a || !workspace || !xyzs || !dirs || !deltas || !ts) { set_error("mfn_march_train_write: null pointer"); return MFN_ERR_ARG; }
-    const float2* stash = (const float2*)((const char*)workspace + ((n_rays * 4 + 255) / 256) * 256);
+    const float2* stash = (const float2*)((const char*)workspace + kWsHeader + ((n_rays * 4 + 255) / 256) * 256);
     const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
     ProfScope ps("march_write", (cudaStream_t)stream);
     march_write_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(rays_o, rays_d, rays_a, stash, max_samples, n_rays,
@@ -191,10 +346,18 @@ extern "C" int mfn_raymarching_train(const float* rays_o, const float* rays_d, c
                                      int cascades, float scale, float exp_step_factor, const float* noise, int grid_size,
                                      int max_samples, int64_t n_rays, int64_t capacity, int64_t* rays_a, float* xyzs, float* dirs,
                                      float* deltas, float* ts, int32_t* counter, void* workspace, int64_t workspace_bytes, void* stream) {
-    int rc = mfn_march_train_count(rays_o, rays_d, hits_t, bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples,
-                                   n_rays, rays_a, counter, workspace, workspace_bytes, stream);
-    if (rc != MFN_OK) return rc;
-    return mfn_march_train_write(rays_o, rays_d, rays_a, workspace, max_samples, n_rays, capacity, xyzs, dirs, deltas, ts, stream);
+    int rc = march_count_impl(rays_o, rays_d, hits_t, bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples,
+                              n_rays, rays_a, counter, workspace, workspace_bytes, stream, false);
+    if (rc != MFN_OK || n_rays == 0) return rc;
+    if (capacity < 0 || (capacity > 0 && (!xyzs || !dirs || !deltas || !ts))) { set_error("mfn_raymarching_train: null pointer"); return MFN_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t* counts = (const int32_t*)((const char*)workspace + kWsHeader);
+    const float2* stash = (const float2*)((const char*)workspace + kWsHeader + ((n_rays * 4 + 255) / 256) * 256);
+    const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
+    ProfScope ps("march_write", st);
+    march_scan_write_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, st>>>(rays_o, rays_d, counts, stash, max_samples, n_rays, capacity, rays_a, counter,
+                                                                       xyzs, dirs, deltas, ts);
+    return check_launch("mfn_raymarching_train", st);
 }
 
 extern "C" int mfn_raymarching_test(const float* rays_o, const float* rays_d, float* hits_t, const int64_t* alive_indices,

@@ -22,6 +22,7 @@ struct MarchConst {
     float dt_min, dt_max, esf;
     float gs, gs_inv, gsm1;   // (float)G, 1/G, G-1
     float scale;              // mip_bound clamp
+    float bound0, bound0_inv; // mip 0: min(2^-1, scale) and its reciprocal
     int cascades, grid_size;
     uint32_t g3;
 };
@@ -37,6 +38,8 @@ __device__ __forceinline__ MarchConst make_march_const(int cascades, int grid_si
     c.gs_inv = __fdiv_rn(1.0f, c.gs);
     c.gsm1 = __fadd_rn(c.gs, -1.0f);
     c.scale = scale;
+    c.bound0 = fminf(0.5f, scale);
+    c.bound0_inv = __fdiv_rn(1.0f, c.bound0);
     c.cascades = cascades;
     c.grid_size = grid_size;
     c.g3 = (uint32_t)grid_size * grid_size * grid_size;
@@ -67,18 +70,25 @@ struct Probe {
 
 // Evaluate one lattice point: position, step, cascade, cell, occupancy bit and (if empty) the t at which
 // the ray leaves the cell.  (ref: raymarching.cu:205-228)
+// ONE_CASCADE: cascades == 1 makes mip = clamp(.., 0, 0) = 0 whatever the position, so the two frexpf and the division are
+// hoisted into MarchConst (bound0 = min(2^-1, scale), bound0_inv = 1/bound0 -- the same IEEE operations, evaluated once).
+template <bool ONE_CASCADE = false>
 __device__ __forceinline__ Probe probe_cell(float t, const RayConst& q, const MarchConst& c, const uint8_t* __restrict__ bitfield) {
     Probe p;
     p.x = __fmaf_rn(q.dx, t, q.ox); p.y = __fmaf_rn(q.dy, t, q.oy); p.z = __fmaf_rn(q.dz, t, q.oz);
     p.dt = march_dt(t, c);
-    int e_pos, e_dt;
-    (void)frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &e_pos);
-    (void)frexpf(__fmul_rn(p.dt, c.gs), &e_dt);
-    const int mip_pos = min(c.cascades - 1, max(0, e_pos + 1));
-    const int mip_dt = min(c.cascades - 1, max(0, e_dt));
-    const int mip = max(mip_pos, mip_dt);
-    const float bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
-    const float bound_inv = __fdiv_rn(1.0f, bound);
+    int mip = 0;
+    float bound = c.bound0, bound_inv = c.bound0_inv;
+    if (!ONE_CASCADE) {
+        int e_pos, e_dt;
+        (void)frexpf(fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z))), &e_pos);
+        (void)frexpf(__fmul_rn(p.dt, c.gs), &e_dt);
+        const int mip_pos = min(c.cascades - 1, max(0, e_pos + 1));
+        const int mip_dt = min(c.cascades - 1, max(0, e_dt));
+        mip = max(mip_pos, mip_dt);
+        bound = fminf(scalbnf(1.0f, mip - 1), c.scale);
+        bound_inv = __fdiv_rn(1.0f, bound);
+    }
     const float fx = __fmul_rn(__fmul_rn(__fmaf_rn(p.x, bound_inv, 1.0f), 0.5f), c.gs);
     const float fy = __fmul_rn(__fmul_rn(__fmaf_rn(p.y, bound_inv, 1.0f), 0.5f), c.gs);
     const float fz = __fmul_rn(__fmul_rn(__fmaf_rn(p.z, bound_inv, 1.0f), 0.5f), c.gs);
@@ -98,54 +108,96 @@ __device__ __forceinline__ Probe probe_cell(float t, const RayConst& q, const Ma
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Warp marcher.  One warp walks one ray; `emit(rank, t, dt)` is called by the lane that owns an accepted
-// sample, rank = its index along the ray.  Stops after `max_emit` samples or when t leaves [0, t2).
-// Returns (warp-uniform) the number of samples emitted; *t_after = t following the last emitted sample.
+// Warp marcher.  One warp walks one ray, 32 lattice points per batch; `emit(rank, t, dt)` is called by the lane
+// that owns an accepted sample, rank = its index along the ray.  Stops after `max_emit` samples or when t leaves
+// [0, t2).  Returns (warp-uniform) the number of samples emitted.
+//
+// Instruction diet (the kernel is issue-bound: every lane-redundant instruction is paid 32 times):
+//   * lattice in O(1) when dt is constant (CONST_DT: exp_step_factor == 0).  Inside one binade the recurrence
+//     t' = fl(t + dt) advances by a constant q = fl(t + dt) - t, so lane j proposes c_j = fma(j, q, t_base) (exact: a
+//     multiple of the binade's ulp) and the warp VERIFIES the recurrence, fl(c_j + dt) == c_{j+1} for all j -- by
+//     induction from c_0 = t_base this proves c_j is the sequential value, bit for bit.  A failed check (binade
+//     crossing, a tie) falls back to the 31-step chain for that batch.
+//   * the landing point of an empty-space skip, "first lattice point with t >= t_target", from the same closed form
+//     (estimate, then an exact +-1 correction against c_j); binary search by shuffles in the fallback.
+//   * the reference's sequential visit order is replayed with warp-uniform bit operations on the ballots; only a skip
+//     needs a shuffle (to fetch the landing index of the lane it starts from).
 // ---------------------------------------------------------------------------------------------------
-template <typename Emit>
+template <bool ONE_CASCADE, bool CONST_DT, typename Emit>
 __device__ __forceinline__ int march_ray_warp(float t_start, float t2, int max_emit, const RayConst& q, const MarchConst& c,
-                                              const uint8_t* __restrict__ bitfield, int lane, Emit emit, float* t_after) {
+                                              const uint8_t* __restrict__ bitfield, int lane, Emit emit) {
+    constexpr uint32_t FULL = 0xffffffffu;
     int n = 0;
     float t_base = t_start;
     float pending = -INFINITY;  // skip target carried over from the previous batch
-    float t_last = t_start;
     // (ref loop condition: 0<=t && t<t2 && N_samples<max_samples, raymarching.cu:204)
     while (t_base >= 0.0f && t_base < t2 && n < max_emit) {
-        // the lattice: every lane walks the same 32-step chain and keeps its own element
-        float tt = t_base, my_t = t_base;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j == lane) my_t = tt;
-            tt = march_next(tt, c);
+        float my_t, t_next_base, qstep = 0.f;
+        bool closed = false;
+        if (CONST_DT) {
+            qstep = __fsub_rn(__fadd_rn(c.dt_min, t_base), t_base);
+            my_t = __fmaf_rn((float)lane, qstep, t_base);
+            const float succ = __fadd_rn(c.dt_min, my_t);                       // what the recurrence gives after my_t
+            const float nxt_c = __shfl_down_sync(FULL, my_t, 1);
+            closed = __all_sync(FULL, lane == 31 || succ == nxt_c);
+            t_next_base = __shfl_sync(FULL, succ, 31);
+        }
+        if (!closed) {   // sequential chain (always for exp_step_factor > 0)
+            float tt = t_base; my_t = t_base;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                if (j == lane) my_t = tt;
+                tt = march_next(tt, c);
+            }
+            t_next_base = tt;
         }
         const bool active = my_t < t2;
         Probe p;
         p.occ = false; p.t_target = 0.f; p.dt = 0.f;
-        if (active) p = probe_cell(my_t, q, c, bitfield);
-        const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
-        const uint32_t occ_mask = __ballot_sync(0xffffffffu, active && p.occ);
-        // first lattice point of this batch that the sequential marcher would visit
+        if (active) p = probe_cell<ONE_CASCADE>(my_t, q, c, bitfield);
+        const uint32_t act_mask = __ballot_sync(FULL, active);
+        const uint32_t occ_mask = __ballot_sync(FULL, active && p.occ);
+        // landing index of a skip that starts from this lane: smallest j > lane with t_j >= t_target, 32 = beyond this batch
+        int land = 32;
+        if (closed) {
+            if (active && !p.occ) {
+                int j = (int)(__fsub_rn(p.t_target, t_base) / qstep);           // estimate; the exact test follows
+                j = max(lane + 1, min(j, 33));
+                // move down while the previous point already satisfies t >= target, then up while this one does not
+                while (j - 1 > lane && __fmaf_rn((float)(j - 1), qstep, t_base) >= p.t_target) --j;
+                while (j < 32 && __fmaf_rn((float)j, qstep, t_base) < p.t_target) ++j;
+                land = min(j, 32);
+            }
+        } else {
+            int lo = lane + 1, hi = 32;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const float tm = __shfl_sync(FULL, my_t, mid < 32 ? mid : 31);
+                if (lo < hi) { if (tm >= p.t_target) hi = mid; else lo = mid + 1; }
+            }
+            land = lo;
+        }
+        // first lattice point of this batch that the sequential marcher visits
         int cur = 0;
         if (pending > -INFINITY) {
-            const uint32_t m = __ballot_sync(0xffffffffu, my_t >= pending);
+            const uint32_t m = __ballot_sync(FULL, my_t >= pending);
             cur = m ? (__ffs(m) - 1) : 32;
             if (cur < 32) pending = -INFINITY;
         }
         uint32_t take = 0;
         bool finished = false;
         while (cur < 32) {
-            if (!((act_mask >> cur) & 1u)) { finished = true; break; }  // t >= t2: ray left the box
-            if ((occ_mask >> cur) & 1u) {
-                const uint32_t rest = ~(occ_mask >> cur);               // run of consecutive occupied points
+            if (!((act_mask >> cur) & 1u)) { finished = true; break; }  // t >= t2: the ray left the box
+            if ((occ_mask >> cur) & 1u) {                                 // run of consecutive occupied points: all taken
+                const uint32_t rest = ~(occ_mask >> cur);
                 const int run = rest ? (__ffs(rest) - 1) : 32;
-                take |= (run >= 32 ? 0xffffffffu : ((1u << run) - 1u)) << cur;
+                take |= (run >= 32 ? FULL : ((1u << run) - 1u)) << cur;
                 cur += run;
-            } else {
-                const float tgt = __shfl_sync(0xffffffffu, p.t_target, cur);
-                const uint32_t later = (cur >= 31) ? 0u : (0xffffffffu << (cur + 1));
-                const uint32_t m = __ballot_sync(0xffffffffu, my_t >= tgt) & later;
-                if (m) cur = __ffs(m) - 1;
-                else { pending = tgt; cur = 32; }
+            } else {                                                      // empty cell: skip to its exit
+                const int nx = __shfl_sync(FULL, land, cur);
+                if (nx >= 32) pending = __shfl_sync(FULL, p.t_target, cur);
+                cur = nx;
             }
         }
         int cnt = __popc(take);
@@ -155,22 +207,131 @@ __device__ __forceinline__ int march_ray_warp(float t_start, float t2, int max_e
                 uint32_t m = take;  // drop the lowest keep-1 set bits; what is left starts at the keep-th one
                 for (int i = 1; i < keep; ++i) m &= m - 1;
                 const int last = __ffs(m) - 1;
-                take &= (last >= 31) ? 0xffffffffu : ((1u << (last + 1)) - 1u);
+                take &= (last >= 31) ? FULL : ((1u << (last + 1)) - 1u);
                 cnt = keep;
             }
             finished = true;
         }
         if ((take >> lane) & 1u) emit(n + __popc(take & ((1u << lane) - 1u)), my_t, p.dt);
-        if (cnt > 0) {
-            const int last_lane = 31 - __clz(take);
-            t_last = __shfl_sync(0xffffffffu, __fadd_rn(p.dt, my_t), last_lane);
-        }
         n += cnt;
         if (finished) break;
-        t_base = tt;
+        t_base = t_next_base;
     }
-    *t_after = t_last;
     return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Group marcher: K lanes (K = 4, 8, 16 or 32) walk one ray, so a warp carries 32/K rays.  Same scheme as the
+// warp marcher -- K consecutive lattice points probed at once, the reference's sequential visit order replayed
+// with (group-local) ballots -- but the work per batch is sized to the empty-space skip length (a skip jumps
+// ~5 lattice points at dt = sqrt(3)/1024 in a 128^3 grid).  The walk is split into a per-group state and a
+// one-batch step so that a group can pick up a new ray as soon as its own is done (march_count_kernel).
+// ---------------------------------------------------------------------------------------------------
+struct GroupState {
+    RayConst q;
+    float t_base, t2, pending;
+    int n;
+    bool alive;     // group-uniform: the ray still has lattice points to visit
+};
+
+__device__ __forceinline__ void group_begin(GroupState& g, const RayConst& q, float t_start, float t2, int max_emit) {
+    g.q = q; g.t_base = t_start; g.t2 = t2; g.pending = -INFINITY; g.n = 0;
+    g.alive = t_start >= 0.0f && t_start < t2 && 0 < max_emit;    // (ref loop condition, raymarching.cu:204)
+}
+
+// One batch of K lattice points for every group of the warp (all 32 lanes must call).  CONST_DT: exp_step_factor == 0, where
+// dt(t) = max(min(t*0, dt_max), dt_min) = dt_min for every finite t >= 0 (bit-identical, one FADD per lattice step).
+template <int K, bool ONE_CASCADE, bool CONST_DT, typename Emit>
+__device__ __forceinline__ void group_step(GroupState& g, int max_emit, const MarchConst& c, const uint8_t* __restrict__ bitfield, int lane, Emit emit) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t KM = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
+    const int sub = lane & (K - 1), gbase = lane & ~(K - 1);
+    // lattice: lane `sub` holds t_base advanced `sub` times
+    float my_t = g.t_base;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) {
+        const float nx = CONST_DT ? __fadd_rn(c.dt_min, my_t) : march_next(my_t, c);
+        if (j < sub) my_t = nx;
+    }
+    const float t_next_base = __shfl_sync(FULL, CONST_DT ? __fadd_rn(c.dt_min, my_t) : march_next(my_t, c), gbase + K - 1);
+    const bool active = g.alive && my_t < g.t2;
+    Probe p;
+    p.occ = false; p.t_target = 0.f; p.dt = 0.f;
+    if (active) p = probe_cell<ONE_CASCADE>(my_t, g.q, c, bitfield);
+    const uint32_t act_mask = (__ballot_sync(FULL, active) >> gbase) & KM;
+    const uint32_t occ_mask = (__ballot_sync(FULL, active && p.occ) >> gbase) & KM;
+    const uint32_t pend_mask = (__ballot_sync(FULL, my_t >= g.pending) >> gbase) & KM;
+    int cur = 0;
+    if (g.pending > -INFINITY) {
+        cur = pend_mask ? (__ffs(pend_mask) - 1) : K;
+        if (cur < K) g.pending = -INFINITY;
+    }
+    // Where does the sequential marcher go after visiting THIS lattice point?  Computed by all lanes at once:
+    //   beyond t2     -> K+1 (the ray is finished when it lands here)
+    //   occupied      -> end of the run of consecutive occupied points (all of them are taken)
+    //   empty         -> first later point with t >= t_target (do { t += dt } while (t < t_target)), K = past this batch
+    unsigned long long hop;   // next index in bits 32.., points taken in bits 0..31 -- one (64-bit) shuffle per hop
+    {
+        int nx; uint32_t runbits = 0;
+        if (!active) nx = K + 1;
+        else if (p.occ) {
+            const uint32_t rest = (~(occ_mask >> sub)) & (KM >> sub);
+            const int run = rest ? (__ffs(rest) - 1) : (K - sub);
+            runbits = ((run >= 32) ? FULL : ((1u << run) - 1u)) << sub;
+            nx = sub + run;
+        } else nx = 0;   // filled in below
+        // binary search over the (ascending) lattice values of the group: smallest j in [sub+1, K) with t_j >= t_target, else K
+        int lo = sub + 1, hi = K;
+#pragma unroll
+        for (int it = 0; (1 << it) < K; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const float tm = __shfl_sync(FULL, my_t, gbase + (mid < K ? mid : K - 1));
+            if (lo < hi) { if (tm >= p.t_target) hi = mid; else lo = mid + 1; }
+        }
+        if (active && !p.occ) nx = lo;
+        hop = ((unsigned long long)(uint32_t)nx << 32) | runbits;
+    }
+    uint32_t take = 0;
+    bool finished = false;
+    int exit_lane = -1;   // >= 0: the batch was left by a skip out of this (empty) lane -> its t_target carries over
+    while (true) {
+        const bool go = g.alive && !finished && cur < K;
+        if (!__any_sync(FULL, go)) break;
+        const unsigned long long h = __shfl_sync(FULL, hop, gbase + (cur < K ? cur : K - 1));
+        if (go) {
+            const int nx = (int)(h >> 32);
+            const uint32_t rb = (uint32_t)h;
+            if (nx > K) finished = true;
+            else {
+                take |= rb;
+                if (nx == K && !rb) exit_lane = cur;
+                cur = nx;
+            }
+        }
+    }
+    {
+        const float tg = __shfl_sync(FULL, p.t_target, gbase + (exit_lane >= 0 ? exit_lane : 0));
+        if (exit_lane >= 0) g.pending = tg;
+    }
+    int cnt = __popc(take);
+    if (g.alive && g.n + cnt >= max_emit) {   // sample budget reached inside this batch: keep the first ones only
+        const int keep = max_emit - g.n;
+        if (cnt > keep) {
+            uint32_t mm = take;
+            for (int i = 1; i < keep; ++i) mm &= mm - 1;
+            const int last = __ffs(mm) - 1;
+            take &= (last >= 31) ? FULL : ((1u << (last + 1)) - 1u);
+            cnt = keep;
+        }
+        finished = true;
+    }
+    if ((take >> sub) & 1u) emit(g.n + __popc(take & ((1u << sub) - 1u)), my_t, p.dt);
+    g.n += cnt;
+    if (finished) g.alive = false;
+    else if (g.alive) {
+        g.t_base = t_next_base;
+        g.alive = g.t_base >= 0.0f && g.t_base < g.t2 && g.n < max_emit;
+    }
 }
 
 // Sequential marcher (one thread per ray) -- the reference's own control flow; used by the test-time
@@ -181,7 +342,7 @@ __device__ __forceinline__ int march_ray_thread(float t, float t2, int max_emit,
     int s = 0;
     float t_last = t;
     while (t < t2 && s < max_emit) {
-        const Probe p = probe_cell(t, q, c, bitfield);
+        const Probe p = probe_cell<false>(t, q, c, bitfield);
         if (p.occ) {
             emit(s, t, p.dt, p.x, p.y, p.z);
             t = __fadd_rn(p.dt, t);

@@ -11,14 +11,21 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 hdr = None
 recs = []
+fname = ""
+seen_files = set()
 for r in rows:
+    if r and r[0] in ("File Path", "File Name"):
+        fname = r[1].split("/")[-1]
+        if fname in seen_files:
+            break          # second launch of the same kernel: first launch only
+        seen_files.add(fname)
+        continue
     if r and r[0] == "Line No":
-        if hdr is not None:
-            break          # first matching launch only
         hdr = r
         continue
     if hdr is None or len(r) < len(hdr) // 2 or not r[0].strip():
         continue          # SASS rows have an empty line number; the source rows carry the roll-up
+    r[1] = fname[:14] + ": " + r[1].strip()
     recs.append(r)
 ix = {h: i for i, h in enumerate(hdr)}
 si = ix["# Samples"]; ii = ix["Instructions Executed"]
