@@ -164,6 +164,92 @@ grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restri
     }
 }
 
+// Backward, second generation (F = 2; used by the fused field path).  Differences from grid_encode_bwd_kernel:
+//   * TWO lanes per sample: lane parity picks the x-corner, so the two corners (x, x+1) of one (y, z) pair -- neighbours in
+//     memory for dense levels and, 7 times out of 8, in the same 32-byte sector for hashed levels (the hash only XORs x into
+//     the low bits) -- travel in the SAME red instruction and are coalesced into one L2 reduction packet: ~45% fewer L2
+//     reduction sectors at the fine levels, which is what bounds this kernel;
+//   * the incoming gradient is read level-major, dT[l][i] (half2), written that way by field_bwd_fused: a warp reads 64
+//     contiguous bytes per level instead of 16 sectors;
+//   * same run aggregation over consecutive samples in the same cell (shuffle distances 2, 4, 8, 16 lanes).
+__global__ void __launch_bounds__(256)
+grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_t* __restrict__ n_dev, const uint32_t* __restrict__ dT, int64_t dT_stride,
+                         const __grid_constant__ GridMeta m, float* __restrict__ dgrid) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int n = n_dev ? min(*n_dev, n_max) : n_max;
+    const int l = blockIdx.y;
+    const int lane = threadIdx.x & 31, xb = lane & 1;
+    const float s = m.scale[l];
+    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const bool hashed = (m.hashed >> l) & 1u;
+    const uint32_t mask = size - 1u, r2 = res * res;
+    float2* lvl = reinterpret_cast<float2*>(dgrid) + m.offset[l];
+    const uint32_t* dl = dT + (size_t)l * dT_stride;
+    const int n_pad = (n + 15) & ~15;   // whole warps stay in the loop (shuffles below)
+    const int step = (int)gridDim.x * (int)(blockDim.x >> 1);
+    for (int i = (int)blockIdx.x * (int)(blockDim.x >> 1) + (int)(threadIdx.x >> 1); i < n_pad; i += step) {
+        uint32_t raw = 0u;
+        if (i < n) raw = __ldg(dl + i);
+        const bool live = (raw & 0x7fff7fffu) != 0u;          // either half non-zero
+        const uint32_t live_mask = __ballot_sync(FULL, live);
+        if (live_mask == 0) continue;
+        uint32_t gx = 0, gy = 0, gz = 0;
+        float v[4][2];   // corners (x = gx + xb, y = gy + (c & 1), z = gz + (c >> 1))
+        if (live) {
+            const float4 p = __ldg(x01 + i);
+            const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+            const float px = fmaf(p.x, s, 0.5f), py = fmaf(p.y, s, 0.5f), pz = fmaf(p.z, s, 0.5f);
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            const float wx = px - fx, wy = py - fy, wz = pz - fz;
+            gx = (uint32_t)(int)fx; gy = (uint32_t)(int)fy; gz = (uint32_t)(int)fz;
+            const float wxs = xb ? wx : 1.f - wx;
+            const float a0 = wxs * (1.f - wy), a1 = wxs * wy;
+            const float w0 = a0 * (1.f - wz), w1 = a1 * (1.f - wz), w2 = a0 * wz, w3 = a1 * wz;
+            v[0][0] = w0 * g.x; v[0][1] = w0 * g.y; v[1][0] = w1 * g.x; v[1][1] = w1 * g.y;
+            v[2][0] = w2 * g.x; v[2][1] = w2 * g.y; v[3][0] = w3 * g.x; v[3][1] = w3 * g.y;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { v[c][0] = 0.f; v[c][1] = 0.f; }
+        }
+        // runs of consecutive live samples in the same cell (the two lanes of a sample share the key)
+        const unsigned long long key = live ? ((unsigned long long)gx | ((unsigned long long)gy << 21) | ((unsigned long long)gz << 42)) : ~0ull;
+        const unsigned long long prev = __shfl_up_sync(FULL, key, 2);
+        const bool head = live && (lane < 2 || prev != key);
+        const uint32_t heads = __ballot_sync(FULL, head && xb == 0);
+        if (heads != (live_mask & 0x55555555u)) {             // at least one run longer than one sample
+            const int my_run = __popc(heads & (FULL >> (31 - lane)));
+#pragma unroll
+            for (int d = 2; d < 32; d <<= 1) {
+                const int other_run = __shfl_down_sync(FULL, my_run, d);
+                const bool take = live && (lane + d < 32) && ((live_mask >> ((lane + d) & 31)) & 1u) && other_run == my_run;
+                if (!__any_sync(FULL, take)) break;    // no run reaches this far: none reaches farther either
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float o0 = __shfl_down_sync(FULL, v[c][0], d), o1 = __shfl_down_sync(FULL, v[c][1], d);
+                    if (take) { v[c][0] += o0; v[c][1] += o1; }
+                }
+            }
+        }
+        if (head) {
+            const uint32_t cx = gx + xb;
+            uint32_t idx[4];
+            if (hashed) {
+                const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+                idx[0] = (cx ^ hy0 ^ hz0) & mask; idx[1] = (cx ^ hy1 ^ hz0) & mask; idx[2] = (cx ^ hy0 ^ hz1) & mask; idx[3] = (cx ^ hy1 ^ hz1) & mask;
+            } else {
+                const uint32_t b = cx + gy * res + gz * r2;
+                idx[0] = b; idx[1] = b + res; idx[2] = b + r2; idx[3] = b + res + r2;
+                if (idx[3] >= size) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) idx[c] %= size;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(lvl + idx[c], make_float2(v[c][0], v[c][1]));
+        }
+    }
+}
+
 // degree-4 real spherical harmonics of v = 2*d01 - 1 (16 outputs)
 __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {  // body shared via sh4.cuh
     sh4_eval(x, y, z, o);
@@ -216,6 +302,15 @@ int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m
     ProfScope ps("grid_encode_fwd", st);
     MFN_F_DISPATCH(F_, (grid_encode_fwd_kernel<F><<<enc_grid(e.n_max, 128, 16), 128, 0, st>>>(e, table, m, out));)
     return check_launch("mfn_grid_encode_fwd", st);
+}
+int grid_scatter_level_major(const float4* x01, int64_t n_max, const int32_t* n_dev, const __half* dT, int64_t dT_stride, const GridMeta& m, float* dgrid,
+                             cudaStream_t st) {
+    if (n_max <= 0) return MFN_OK;
+    if (n_max > 0x7fffffff) { set_error("mfn_field_bwd: more than 2^31 samples"); return MFN_ERR_ARG; }
+    dim3 grid(enc_grid(n_max, 128, 8), (unsigned)m.n_levels);
+    ProfScope ps("grid_encode_bwd", st);
+    grid_scatter_pair_kernel<<<grid, 256, 0, st>>>(x01, (int)n_max, n_dev, reinterpret_cast<const uint32_t*>(dT), dT_stride, m, dgrid);
+    return check_launch("mfn_grid_encode_bwd(level-major)", st);
 }
 int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F_, float* dgrid, int32_t* overflow_flag, cudaStream_t st) {
     if (e.n_max <= 0) return MFN_OK;

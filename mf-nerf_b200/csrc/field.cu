@@ -18,15 +18,16 @@ static bool use_fused(const mfn_field_cfg* c) {
 }
 
 // workspace of the fused path: [tile blobs | rgb copy (n,3) f32 | dfeats (n,32) f16 | weight-gradient partials]
-struct FusedWs { size_t blobs, rgb, dfeats, partials, total; };
+struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, total; };
 static FusedWs fused_ws(int64_t n, bool training) {
     FusedWs w{};
     size_t o = 0;
     if (training) {
         w.blobs = o; o += fused_blob_bytes(n);
         w.rgb = o; o += (size_t)(n * 12 + 255) / 256 * 256;
-        w.dfeats = o; o += (size_t)(n * 64 + 255) / 256 * 256;
+        w.dfeats = o; o += (size_t)((n + 63) / 64 * 64) * 64;
         w.partials = o; o += (fused_partial_bytes() + 255) / 256 * 256;
+        w.x01 = o; o += (size_t)(n * 16 + 255) / 256 * 256;
     }
     w.total = o > 256 ? o : 256;
     return w;
@@ -185,7 +186,7 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         const bool train = (size_t)workspace_bytes >= fw.total;
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
         f.sigmas = sigmas; f.rgbs = rgbs;
-        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); }
+        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.x01 = (float4*)(ws + fw.x01); }
         return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;
@@ -224,10 +225,10 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         if ((size_t)workspace_bytes < fw.total) { set_error("mfn_field_bwd: workspace too small"); return MFN_ERR_ARG; }
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, nullptr, n_max, n_dev);
         f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.dfeats = (__half*)(ws + fw.dfeats);
+        f.dfeats_stride = (n_max + 63) / 64 * 64;
         f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
         if ((rc = fused_field_backward(f, cfg->rgb_hidden, d_xyz_params, d_rgb_params, st)) != MFN_OK) return rc;
-        EncArgs e; make_enc(e, cfg, xyzs, n_max, n_dev);
-        return grid_encode_backward(e, f.dfeats, m, cfg->grid.n_features, d_xyz_params + 64 * 32 + 16 * 64, overflow_flag, st);
+        return grid_scatter_level_major((const float4*)(ws + fw.x01), n_max, n_dev, f.dfeats, f.dfeats_stride, m, d_xyz_params + 64 * 32 + 16 * 64, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;

@@ -179,6 +179,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
                 y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
                 z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
+                if (MODE == 1 && hsel == 1) a.x01[i] = make_float4(x, y, z, 0.f);
             }
 #pragma unroll 2
             for (int j = 0; j < 8; ++j) {
@@ -496,19 +497,20 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
         tc_fence_after();
-        {   // dX row -> dfeats (n, 32) fp16
+        {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel
             uint32_t r[32];
             tmem_ld_x32(trow + kAccH, r);
             tmem_ld_wait();
             if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(a.dfeats + (size_t)i * 32);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.dfeats) + i;
+                bool ovf = false;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 o;
-                    o.x = pack2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])); o.y = pack2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                    o.z = pack2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])); o.w = pack2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-                    dst[c] = o;
+                for (int l = 0; l < 16; ++l) {
+                    const uint32_t h2 = pack2(__uint_as_float(r[2 * l]), __uint_as_float(r[2 * l + 1]));
+                    ovf |= ((h2 & 0x7c00u) == 0x7c00u) || ((h2 & 0x7c000000u) == 0x7c000000u);   // inf / nan in either half
+                    dst[(size_t)l * a.dfeats_stride] = h2;
                 }
+                bad |= ovf;
             }
         }
         acc = 1u;

@@ -45,6 +45,10 @@ struct EncArgs {
     int64_t n_max; const int32_t* n_dev;
 };
 int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m, int F, __half* out, cudaStream_t st);
+// dT: level-major gradient [L][dT_stride] of half2 (F = 2), loss-scaled
+// x01: normalised positions (n,4) f32 (w unused)
+int grid_scatter_level_major(const float4* x01, int64_t n_max, const int32_t* n_dev, const __half* dT, int64_t dT_stride, const GridMeta& m, float* dgrid,
+                             cudaStream_t st);
 int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F, float* dgrid, int32_t* overflow_flag, cudaStream_t st);
 
 // ---- fused tcgen05 field kernels (field_fused.cu) ----
@@ -61,7 +65,9 @@ struct FusedArgs {
     int rgb_act;
     // backward only
     const float* dL_dsigmas; const float* dL_drgbs; float loss_scale;
-    __half* dfeats;          // (n, 32) fp16 row-major, loss-scaled
+    __half* dfeats;          // level-major [16][dfeats_stride] half2, loss-scaled
+    int64_t dfeats_stride;
+    float4* x01;             // training: normalised positions (n,4) f32, written by the forward kernel for the scatter kernel
     float* partials;         // [gridDim.x][10240] per-CTA weight gradients
     int32_t* overflow;
 };
