@@ -115,6 +115,48 @@ __device__ __forceinline__ uint32_t gather_level(const uint32_t* __restrict__ ta
     return pack2(f0, f1);
 }
 
+// Lane-pair variant: the two lanes of a pair work on the same sample and each fetches the 4 corners of ITS x (gx + xb), so the
+// corners (x, x+1) of one (y, z) -- same 32-byte sector 7 times out of 8 -- are requested by the same load instruction: a warp's
+// gather touches <= 16 sectors instead of <= 32, and the L1 sector rate is what bounds this phase.  Returns the pair's sum.
+__device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb) {
+    const float s = m.scale[l];
+    const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
+    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const float wx = px - fx, wy = py - fy, wz = pz - fz;
+    const uint32_t cx = (uint32_t)(int)fx + (uint32_t)xb, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const uint32_t* lvl = table + off;
+    uint32_t idx[4];
+    if ((m.hashed >> l) & 1u) {
+        const uint32_t mask = size - 1u;
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+        idx[0] = (cx ^ hy0 ^ hz0) & mask; idx[1] = (cx ^ hy1 ^ hz0) & mask; idx[2] = (cx ^ hy0 ^ hz1) & mask; idx[3] = (cx ^ hy1 ^ hz1) & mask;
+    } else {
+        const uint32_t r2 = res * res;
+        const uint32_t b = cx + gy * res + gz * r2;
+        idx[0] = b; idx[1] = b + res; idx[2] = b + r2; idx[3] = b + res + r2;
+        if (idx[3] >= size) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) idx[c] %= size;
+        }
+    }
+    uint32_t v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = __ldg(lvl + idx[c]);
+    const float wxs = xb ? wx : 1.f - wx;
+    const float a0 = wxs * (1.f - wy), a1 = wxs * wy;
+    const float w[4] = {a0 * (1.f - wz), a1 * (1.f - wz), a0 * wz, a1 * wz};
+    float f0 = 0.f, f1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v[c]));
+        f0 = fmaf(w[c], f.x, f0); f1 = fmaf(w[c], f.y, f1);
+    }
+    f0 += __shfl_xor_sync(0xffffffffu, f0, 1);
+    f1 += __shfl_xor_sync(0xffffffffu, f1, 1);
+    return pack2(f0, f1);
+}
+
 __device__ __forceinline__ float act_out(float x, int act) {
     if (act == MFN_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
     if (act == MFN_ACT_EXP) return __expf(x);
@@ -171,21 +213,23 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
         unsigned char* blob = (MODE == 1) ? a.blobs + (size_t)tile * kBlob : nullptr;
-        // ---- hash-grid gather -> X tile (levels 8*hsel .. 8*hsel+7 of this thread's row)
+        // ---- hash-grid gather -> X tile: lane pair (2p, 2p+1) of warp w works on row 16w + p, all 16 levels
         {
+            const int grow = tid >> 1, xb = tid & 1;
+            const int64_t gi = tile * kFT + grow;
+            const bool gvalid = gi < n;
             float x = 0.5f, y = 0.5f, z = 0.5f;
-            if (valid) {
-                x = a.xyzs[3 * i]; y = a.xyzs[3 * i + 1]; z = a.xyzs[3 * i + 2];
+            if (gvalid) {
+                x = a.xyzs[3 * gi]; y = a.xyzs[3 * gi + 1]; z = a.xyzs[3 * gi + 2];
                 x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
                 y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
                 z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
-                if (MODE == 1 && hsel == 1) a.x01[i] = make_float4(x, y, z, 0.f);
+                if (MODE == 1 && xb == 1) a.x01[gi] = make_float4(x, y, z, 0.f);
             }
 #pragma unroll 2
-            for (int j = 0; j < 8; ++j) {
-                const int l = 8 * hsel + j;
-                const uint32_t v = valid ? gather_level(table, m, l, x, y, z) : 0u;
-                *reinterpret_cast<uint32_t*>(smem + kFwdX + tile_off(row, 2 * l, 32)) = v;
+            for (int l = 0; l < 16; ++l) {
+                const uint32_t v = gather_level_pair(table, m, l, x, y, z, xb);    // (invalid rows gather entry 0 harmlessly)
+                if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + kFwdX + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
             }
         }
         // ---- SH of the normalised direction -> CAT[:, 0:16]   (networks.py:145-146)
