@@ -14,6 +14,7 @@
 #include "field_internal.h"
 #include "grid_common.cuh"
 #include "sh4.cuh"
+#include "umma.cuh"
 #include <math.h>
 
 namespace mfn {
@@ -186,6 +187,7 @@ grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_
     float2* lvl = reinterpret_cast<float2*>(dgrid) + m.offset[l];
     const uint32_t* dl = dT + (size_t)l * dT_stride;
     const int n_pad = (n + 15) & ~15;   // whole warps stay in the loop (shuffles below)
+    const uint64_t pol_keep = umma::policy_evict_last();   // gradient table lines stay in L2 while the other levels / kernels stream
     const int step = (int)gridDim.x * (int)(blockDim.x >> 1);
     for (int i = (int)blockIdx.x * (int)(blockDim.x >> 1) + (int)(threadIdx.x >> 1); i < n_pad; i += step) {
         uint32_t raw = 0u;
@@ -245,7 +247,7 @@ grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) atomicAdd(lvl + idx[c], make_float2(v[c][0], v[c][1]));
+            for (int c = 0; c < 4; ++c) umma::red_add_v2_hint(lvl + idx[c], v[c][0], v[c][1], pol_keep);
         }
     }
 }

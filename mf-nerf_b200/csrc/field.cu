@@ -187,6 +187,7 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
         f.sigmas = sigmas; f.rgbs = rgbs;
         if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.x01 = (float4*)(ws + fw.x01); }
+        { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;

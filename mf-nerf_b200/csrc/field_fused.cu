@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t gather_level(const uint32_t* __restrict__ ta
 // Lane-pair variant: the two lanes of a pair work on the same sample and each fetches the 4 corners of ITS x (gx + xb), so the
 // corners (x, x+1) of one (y, z) -- same 32-byte sector 7 times out of 8 -- are requested by the same load instruction: a warp's
 // gather touches <= 16 sectors instead of <= 32, and the L1 sector rate is what bounds this phase.  Returns the pair's sum.
-__device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb) {
+__device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb, uint64_t pol) {
     const float s = m.scale[l];
     const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
@@ -142,7 +142,7 @@ __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict
     }
     uint32_t v[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = __ldg(lvl + idx[c]);
+    for (int c = 0; c < 4; ++c) v[c] = ldg_nc_hint(lvl + idx[c], pol);   // the table is to stay L2-resident (evict_last)
     const float wxs = xb ? wx : 1.f - wx;
     const float a0 = wxs * (1.f - wy), a1 = wxs * wy;
     const float w[4] = {a0 * (1.f - wz), a1 * (1.f - wz), a0 * wz, a1 * wz};
@@ -185,6 +185,8 @@ __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* t
 // gather phase and the 64 accumulator columns in the hidden-layer epilogues.  In training mode every published tile is also sent
 // to the blob with one bulk async store (shared -> global) issued by thread 0.
 constexpr int kFwdThreads = 256;
+// phase timestamps of CTA 0 (tools/fwd_phases.py): a.dbg != nullptr only in that tool
+#define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
 
 template <int NH2, int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 4)
@@ -208,11 +210,14 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const uint32_t sbase = smem_u32(smem);
     uint32_t phase = 0;
     const uint32_t* table = reinterpret_cast<const uint32_t*>(a.table);
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tile_no = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
         unsigned char* blob = (MODE == 1) ? a.blobs + (size_t)tile * kBlob : nullptr;
+        MFN_TS(0);
         // ---- hash-grid gather -> X tile: lane pair (2p, 2p+1) of warp w works on row 16w + p, all 16 levels
         {
             const int grow = tid >> 1, xb = tid & 1;
@@ -228,7 +233,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             }
 #pragma unroll 2
             for (int l = 0; l < 16; ++l) {
-                const uint32_t v = gather_level_pair(table, m, l, x, y, z, xb);    // (invalid rows gather entry 0 harmlessly)
+                const uint32_t v = gather_level_pair(table, m, l, x, y, z, xb, pol_keep);    // (invalid rows gather entry 0 harmlessly)
                 if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + kFwdX + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
             }
         }
@@ -247,31 +252,36 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 0, 32)) = o0;
             *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 8, 32)) = o1;
         }
+        MFN_TS(1); MFN_TS(109);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MFN_TS(2);
         // ---- layer 1: H1 = relu(X . W1^T)
         if (tid == 0) {
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g(blob + kBX, smem + kFwdX, kFT * 32 * 2); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + kFwdX, kFT * 32 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
+        MFN_TS(3);
         tc_fence_after();
         relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
+        MFN_TS(4);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MFN_TS(5);
         // ---- layer 2: h = H1 . W2^T (16 outputs, no activation); sigma = exp(h0)  (TruncExp forward)
         if (tid == 0) {
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g(blob + kBH1, smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -292,9 +302,11 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             }
         }
         phase ^= 1u;
+        MFN_TS(6);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        MFN_TS(7);
         if (MODE == 2) continue;   // (uniform) density only
         // ---- rgb layer 1: H2 = relu(CAT . W3^T)
         if (tid == 0) {
@@ -302,7 +314,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g(blob + kBC, smem + kFwdC, kFT * 32 * 2); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + kBC, smem + kFwdC, kFT * 32 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -318,7 +330,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
                 for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
-                if (MODE == 1) { bulk_s2g(blob + kBH2, smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
+                if (MODE == 1) { bulk_s2g_hint(blob + kBH2, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
                 mma_commit(&bar);
             }
             mbar_wait(&bar, phase); phase ^= 1u;
@@ -334,7 +346,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -355,6 +367,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         phase ^= 1u;
         tc_fence_before();
         __syncthreads();   // TMEM and the tiles are free for the next tile
+        MFN_TS(8);
     }
     if (MODE == 1 && tid == 0) bulk_wait0();
     tc_fence_before();
@@ -420,7 +433,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         const bool valid = i < n;
         if (tid == 0) {   // the whole activation blob of this tile with one bulk async copy
             mbar_arrive_expect_tx(&bar_load, NH2 == 2 ? kBlob : kBH3);
-            bulk_g2s(sBlob, a.blobs + (size_t)tile * kBlob, NH2 == 2 ? kBlob : kBH3, &bar_load);
+            bulk_g2s_hint(sBlob, a.blobs + (size_t)tile * kBlob, NH2 == 2 ? kBlob : kBH3, &bar_load, policy_evict_first());
         }
         // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
         {

@@ -70,6 +70,7 @@ struct FusedArgs {
     float4* x01;             // training: normalised positions (n,4) f32, written by the forward kernel for the scatter kernel
     float* partials;         // [gridDim.x][10240] per-CTA weight gradients
     int32_t* overflow;
+    long long* dbg;          // optional phase timestamps (tools only)
 };
 bool fused_field_supported(const mfn_field_cfg* c);
 size_t fused_blob_bytes(int64_t n_max);

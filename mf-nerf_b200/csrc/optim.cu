@@ -3,6 +3,7 @@
 // skip-on-overflow (GradScaler semantics), refresh of the fp16 shadow parameters the field kernels read, and
 // zeroing of the gradient buffer for the next step.  HBM-bound: 30 B/param (p,g,m,v read; p,m,v,p16 written; g zeroed).
 #include "common.cuh"
+#include "umma.cuh"
 #include "../../include/mfnerf_b200.h"
 
 namespace mfn {
@@ -11,6 +12,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, __half* __restrict__ p_h, int64_t n,
             float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale, const int32_t* __restrict__ skip_flag, int zero_grad) {
     const bool skip = skip_flag && *skip_flag != 0;
+    const uint64_t pol_keep = umma::policy_evict_last();   // the fp16 shadow (hash table + weights) is what the next step gathers from: keep it in L2
     const int64_t n4 = n / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -28,7 +30,7 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
             reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
             if (p_h) {
                 __half2 lo = __floats2half2_rn(pp.x, pp.y), hi = __floats2half2_rn(pp.z, pp.w);
-                reinterpret_cast<uint2*>(p_h)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                umma::st_hint_b64(reinterpret_cast<uint2*>(p_h) + i, *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi), pol_keep);
             }
         }
         if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
