@@ -376,16 +376,17 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------------ backward
+constexpr int kBwdThreads = 256;
+
 // TMEM (fp32 dgrad accumulator) -> mask with relu'(activation tile row) -> fp16 dZ row written IN PLACE of the activation row
-__device__ __forceinline__ void mask_epilogue64(uint32_t taddr, unsigned char* tile, int row) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+__device__ __forceinline__ void mask_epilogue32(uint32_t taddr, unsigned char* tile, int row, int col0) {
+    {
         uint32_t r[32];
-        tmem_ld_x32(taddr + half * 32, r);
+        tmem_ld_x32(taddr + col0, r);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            uint4* p = reinterpret_cast<uint4*>(tile + tile_off(row, half * 32 + c * 8, 64));
+            uint4* p = reinterpret_cast<uint4*>(tile + tile_off(row, col0 + c * 8, 64));
             const uint4 act = *p;
             const __half2* ah = reinterpret_cast<const __half2*>(&act);
             uint4 o;
@@ -401,15 +402,16 @@ __device__ __forceinline__ void mask_epilogue64(uint32_t taddr, unsigned char* t
 }
 
 template <int NH2>
-__global__ void __launch_bounds__(kFT, 2)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_mma, bar_load;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (kFT - 1), hsel = tid >> 7;   // two threads per sample row: they split the accumulator columns
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
-    stage_all_weights<NH2>(smem, a, tid, kFT, true);
+    stage_all_weights<NH2>(smem, a, tid, kBwdThreads, true);
     if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_load, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, kBwdCols);
     fence_async_smem();
@@ -417,7 +419,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base_s;
-    const uint32_t trow = tmem_addr(tbase, warp * 32, 0);
+    const uint32_t trow = tmem_addr(tbase, (warp & 3) * 32, 0);
     const uint32_t sbase = smem_u32(smem);
     unsigned char* sBlob = smem + kBwdBlob;
     const uint32_t sX = sbase + kBwdBlob + kBX, sH1 = sbase + kBwdBlob + kBH1, sC = sbase + kBwdBlob + kBC, sH2 = sbase + kBwdBlob + kBH2,
@@ -429,14 +431,14 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     bool bad = false;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t i = tile * kFT + tid;
+        const int64_t i = tile * kFT + row;
         const bool valid = i < n;
         if (tid == 0) {   // the whole activation blob of this tile with one bulk async copy
             mbar_arrive_expect_tx(&bar_load, NH2 == 2 ? kBlob : kBH3);
             bulk_g2s_hint(sBlob, a.blobs + (size_t)tile * kBlob, NH2 == 2 ? kBlob : kBH3, &bar_load, policy_evict_first());
         }
         // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
-        {
+        if (hsel == 0) {
             float g[3] = {0.f, 0.f, 0.f};
             if (valid) {
 #pragma unroll
@@ -451,8 +453,8 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             uint4 o0 = make_uint4(pack2(g[0], g[1]), pack2(g[2], 0.f), 0u, 0u);
             const __half2* hh = reinterpret_cast<const __half2*>(&o0);
             bad |= !isfinite(__low2float(hh[0])) || !isfinite(__high2float(hh[0])) || !isfinite(__low2float(hh[1]));
-            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 0, 16)) = o0;
-            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 0, 16)) = o0;
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
         }
         mbar_wait(&bar_load, ph_load); ph_load ^= 1u;
         fence_async_smem();
@@ -469,7 +471,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
         tc_fence_after();
-        mask_epilogue64(trow + kAccH, pHL, tid);                 // dZ of the last hidden layer, in place
+        mask_epilogue32(trow + kAccH, pHL, row, 32 * hsel);                 // dZ of the last hidden layer, in place
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -487,7 +489,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             }
             mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
             tc_fence_after();
-            mask_epilogue64(trow + kAccH, sBlob + kBH2, tid);    // dZ3 in place of H2
+            mask_epilogue32(trow + kAccH, sBlob + kBH2, row, 32 * hsel);    // dZ3 in place of H2
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -505,13 +507,13 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
         tc_fence_after();
-        {   // dh = dCAT[:, 16:32] ; dh[0] += loss_scale * dL/dsigma * exp(clamp(h0, -15, 15))   (TruncExp backward)
+        if (hsel == 0) {   // dh = dCAT[:, 16:32] ; dh[0] += loss_scale * dL/dsigma * exp(clamp(h0, -15, 15))   (TruncExp backward)
             uint32_t r[16];
             tmem_ld_x16(trow + kAccH + 16, r);
             tmem_ld_wait();
             float d0 = __uint_as_float(r[0]);
             if (valid) {
-                const float h0 = __half2float(*reinterpret_cast<const __half*>(sBlob + kBC + tile_off(tid, 16, 32)));
+                const float h0 = __half2float(*reinterpret_cast<const __half*>(sBlob + kBC + tile_off(row, 16, 32)));
                 d0 += a.dL_dsigmas[i] * expf(fminf(fmaxf(h0, -15.f), 15.f)) * a.loss_scale;
             }
             uint4 o0, o1;
@@ -520,8 +522,8 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9])); o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
             o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
             bad |= !isfinite(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
-            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 0, 16)) = o0;
-            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(tid, 8, 16)) = o1;
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 0, 16)) = o0;
+            *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 8, 16)) = o1;
         }
         fence_async_smem();
         tc_fence_before();
@@ -537,7 +539,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
         tc_fence_after();
-        mask_epilogue64(trow + kAccH, sBlob + kBH1, tid);        // dZ1 in place of H1
+        mask_epilogue32(trow + kAccH, sBlob + kBH1, row, 32 * hsel);        // dZ1 in place of H1
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -554,15 +556,15 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
         tc_fence_after();
-        {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel
-            uint32_t r[32];
-            tmem_ld_x32(trow + kAccH, r);
+        {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel; each thread of a row does 8 levels
+            uint32_t r[16];
+            tmem_ld_x16(trow + kAccH + 16 * hsel, r);
             tmem_ld_wait();
             if (valid) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(a.dfeats) + i;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(a.dfeats) + i + (size_t)(8 * hsel) * a.dfeats_stride;
                 bool ovf = false;
 #pragma unroll
-                for (int l = 0; l < 16; ++l) {
+                for (int l = 0; l < 8; ++l) {
                     const uint32_t h2 = pack2(__uint_as_float(r[2 * l]), __uint_as_float(r[2 * l + 1]));
                     ovf |= ((h2 & 0x7c00u) == 0x7c00u) || ((h2 & 0x7c000000u) == 0x7c000000u);   // inf / nan in either half
                     dst[(size_t)l * a.dfeats_stride] = h2;
@@ -579,8 +581,8 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     // ---- flush this CTA's weight-gradient accumulators (M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16)
     float* part = a.partials + (size_t)blockIdx.x * kNumWg;
     if (acc == 0u) {
-        for (int q = tid; q < kNumWg; q += kFT) part[q] = 0.f;
-    } else {
+        for (int q = tid; q < kNumWg; q += kBwdThreads) part[q] = 0.f;
+    } else if (warp < 4) {
         tc_fence_after();
         const int mrow = warp * 16 + (lane & 15);
         const bool own = lane < 16;
@@ -612,13 +614,27 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     if (warp == 0) tmem_dealloc(tbase, kBwdCols);
 }
 
-// d_params[j] += sum over CTAs of partials[c][j]; the first 3072 entries belong to the sigma net, the rest to the rgb net
-__global__ void reduce_wgrad_kernel(const float* __restrict__ partials, int n_parts, int n_rgb, float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= 3072 + n_rgb) return;
-    float s = 0.f;
-    for (int c = 0; c < n_parts; ++c) s += partials[(size_t)c * kNumWg + j];
-    if (j < 3072) d_sigma[j] += s; else d_rgb[j - 3072] += s;
+// d_params[j] += sum over CTAs of partials[c][j]; the first 3072 entries belong to the sigma net, the rest to the rgb net.
+// block = 32 outputs x 8 slices of the partial list (coalesced 128-byte rows, 8 independent accumulation chains per output)
+__global__ void __launch_bounds__(256)
+reduce_wgrad_kernel(const float* __restrict__ partials, int n_parts, int n_rgb, float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
+    __shared__ float sm[8][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f;
+    if (j < 3072 + n_rgb) {
+        int c = slice;
+        for (; c + 8 < n_parts; c += 16) { s0 += partials[(size_t)c * kNumWg + j]; s1 += partials[(size_t)(c + 8) * kNumWg + j]; }
+        if (c < n_parts) s0 += partials[(size_t)c * kNumWg + j];
+    }
+    sm[slice][lane] = s0 + s1;
+    __syncthreads();
+    if (slice == 0 && j < 3072 + n_rgb) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][lane];
+        if (j < 3072) d_sigma[j] += t; else d_rgb[j - 3072] += t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host side
@@ -665,7 +681,7 @@ static int launch_bwd(const FusedArgs& a, cudaStream_t st) {
     const int64_t tiles = ceil_div(a.n_max, kFT);
     const int64_t cap = fused_bwd_max_ctas();
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    field_bwd_fused_kernel<NH2><<<grid, kFT, kBwdSmem, st>>>(a);
+    field_bwd_fused_kernel<NH2><<<grid, kBwdThreads, kBwdSmem, st>>>(a);
     return (int)grid;
 }
 
@@ -680,7 +696,7 @@ int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_para
     const int n_rgb = 64 * 32 + (rgb_hidden - 1) * 64 * 64 + 16 * 64;
     {
         ProfScope ps("reduce_wgrad", st);
-        reduce_wgrad_kernel<<<(3072 + n_rgb + 127) / 128, 128, 0, st>>>(a.partials, grid, n_rgb, d_sigma_params, d_rgb_params);
+        reduce_wgrad_kernel<<<(3072 + n_rgb + 31) / 32, 256, 0, st>>>(a.partials, grid, n_rgb, d_sigma_params, d_rgb_params);
     }
     return check_launch("mfn_field_bwd(reduce)", st);
 }
