@@ -331,7 +331,8 @@ def run_ours(args):
             e0.record(); out = eng.render(o, d); e1.record(); torch.cuda.synchronize(dev)
             frames.append(e0.elapsed_time(e1))
         ms_frame = float(np.mean(frames[1:]))
-        render = {"fps_800x800": 1e3 / ms_frame, "ms_per_frame": ms_frame, "samples_per_ray": float(out["total_samples"]) / (800 * 800)}
+        render = {"fps_800x800": 1e3 / ms_frame, "ms_per_frame": ms_frame, "samples_per_ray": float(out["total_samples"]) / (800 * 800),
+                  "iterations": out.get("iterations"), "field_rows_per_ray": out.get("field_rows", 0) / (800 * 800)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -178,6 +178,25 @@ int mfn_field_bwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const
 int mfn_density_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
                     float* sigmas, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- test-time rendering without host round trips (replaces the while-loop of __render_rays_test, rendering.py:46-118) ----------
+ * The alive list, its length, N_samples = clamp(N_rays / N_alive, min_samples, 64) and the max_samples budget live in the
+ * workspace; one iteration = plan -> march (raymarching_test semantics) -> field -> composite (composite_test_fw semantics)
+ * + compaction of the surviving rays.  Call _begin once (AABB test + near clamp, rendering.py:27-29, outputs zeroed), then
+ * _iterations in batches until mfn_render_status reports no alive rays, then _finish (rgb += bg * (1 - opacity), l.112-116).
+ * center_host / half_size_host / bg_rgb_host: 3 floats in HOST memory.  Needs the field shape the fused kernels cover. */
+int64_t mfn_render_workspace_bytes(int64_t n_rays, int min_samples);
+int mfn_render_begin(const float* rays_o, const float* rays_d, const float* center_host, const float* half_size_host, int64_t n_rays,
+                     float near_distance, int min_samples, float* opacity, float* depth, float* rgb, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+int mfn_render_iterations(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* rays_o, const float* rays_d,
+                          int64_t n_rays, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor, int grid_size,
+                          int max_samples, int min_samples, float T_threshold, int n_iterations, float* opacity, float* depth, float* rgb,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+/* asynchronously copies 10 int32 {n_alive[0], n_alive[1], current list, N_samples, rows, samples spent, iterations, field rows / 1024, total N_eff lo, hi}
+ * to HOST (pinned) memory */
+int mfn_render_status(const void* workspace, int32_t* status_host_pinned, void* stream);
+int mfn_render_finish(float* rgb, const float* opacity, const float* bg_rgb_host, int64_t n_rays, void* stream);
+
 /* ---- per-ray loss (losses.py:47-60 NeRFLoss + train.py:178 + background blend rendering.py:153-161) --------------- */
 /* loss = mean((rgb + bg*(1-opacity) - target)^2) + mean(lambda_o * -(o+1e-10)*log(o+1e-10)) [+ mean(lambda_d * distortion)].
  * Writes the gradients w.r.t. rgb (n,3), opacity (n) and, if distortion != NULL, the per-ray distortion loss (n), each

@@ -318,7 +318,40 @@ class NGPEngine:
 
     # ------------------------------------------------------------------------------------------------ test-time rendering
     @torch.no_grad()
-    def render(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4):
+    def render(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4, iterations_per_batch=8):
+        """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples): the device-side
+        wavefront of csrc/render.cu.  The host only looks at the alive count between batches of `iterations_per_batch` iterations."""
+        d = self.dev
+        N = rays_o.shape[0]
+        rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
+        min_samples = 1 if self.esf == 0 else 4
+        need = _lib.lib.mfn_render_workspace_bytes(N, min_samples)
+        if getattr(self, "_render_ws", None) is None or self._render_ws.numel() < need:
+            self._render_ws = torch.empty(need, dtype=torch.uint8, device=d)
+            self._render_status = torch.zeros(10, dtype=torch.int32).pin_memory()
+        ws, status = self._render_ws, self._render_status
+        opacity = torch.empty(N, device=d); depth = torch.empty(N, device=d); rgb = torch.empty(N, 3, device=d)
+        center = (ctypes.c_float * 3)(0.0, 0.0, 0.0); half = (ctypes.c_float * 3)(self.scale, self.scale, self.scale)
+        st = stream_ptr(d)
+        call("mfn_render_begin", ptr(rays_o), ptr(rays_d), center, half, N, NEAR_DISTANCE, min_samples, ptr(opacity), ptr(depth), ptr(rgb), ptr(ws), ws.numel(), st)
+        cfg = ctypes.byref(self.cfg)
+        done_evt = torch.cuda.Event()
+        while True:
+            call("mfn_render_iterations", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(rays_o), ptr(rays_d), N, ptr(self.density_bitfield),
+                 self.cascades, self.scale, self.esf, G, int(max_samples), min_samples, float(T_threshold), int(iterations_per_batch), ptr(opacity), ptr(depth),
+                 ptr(rgb), ptr(ws), ws.numel(), st)
+            call("mfn_render_status", ptr(ws), status.data_ptr(), st)
+            done_evt.record(torch.cuda.current_stream(d))
+            done_evt.synchronize()
+            s = status.tolist()
+            if s[s[2]] == 0 or s[5] >= max_samples:
+                break
+        call("mfn_render_finish", ptr(rgb), ptr(opacity), self.bg, N, st)
+        total = (s[8] & 0xffffffff) | (s[9] << 32)
+        return {"rgb": rgb, "depth": depth, "opacity": opacity, "total_samples": total, "iterations": s[6], "field_rows": s[7] * 1024}
+
+    @torch.no_grad()
+    def render_reference_loop(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4):
         """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples)"""
         import vren
         d = self.dev
