@@ -20,6 +20,7 @@
 #include "grid_common.cuh"
 #include "sh4.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 
 namespace mfn {
 using namespace umma;
@@ -662,7 +663,9 @@ static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
     static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
-    const int64_t cap = 4 * (int64_t)num_sms();
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) { const char* e = getenv("MFN_FWD_CTAS"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1 || ctas_per_sm > 4) ctas_per_sm = 4; }
+    const int64_t cap = ctas_per_sm * (int64_t)num_sms();
     field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, kFwdSmem, st>>>(a, m);
 }
 

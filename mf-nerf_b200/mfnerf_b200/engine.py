@@ -318,13 +318,13 @@ class NGPEngine:
 
     # ------------------------------------------------------------------------------------------------ test-time rendering
     @torch.no_grad()
-    def render(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4, iterations_per_batch=8):
+    def render(self, rays_o, rays_d, max_samples=MAX_SAMPLES, T_threshold=1e-4, iterations_per_batch=8, min_chunk=None):
         """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples): the device-side
         wavefront of csrc/render.cu.  The host only looks at the alive count between batches of `iterations_per_batch` iterations."""
         d = self.dev
         N = rays_o.shape[0]
         rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
-        min_samples = 1 if self.esf == 0 else 4
+        min_samples = (1 if self.esf == 0 else 4) if min_chunk is None else int(min_chunk)     # rendering.py:70
         need = _lib.lib.mfn_render_workspace_bytes(N, min_samples)
         if getattr(self, "_render_ws", None) is None or self._render_ws.numel() < need:
             self._render_ws = torch.empty(need, dtype=torch.uint8, device=d)
