@@ -21,11 +21,12 @@ __device__ __forceinline__ float alpha_of(float sigma, float delta) { return __f
 // after the whole chunk (identical in all lanes).
 __device__ __forceinline__ float chunk_transmittance(float a, float T_in, int lane, float* t_end) {
     float Tj = T_in, mine = T_in;
+    const float om = __fadd_rn(1.0f, -a);      // (1 - a_j) is rounded once per sample, exactly as in the sequential loop
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const float aj = __shfl_sync(0xffffffffu, a, j);
+        const float omj = __shfl_sync(0xffffffffu, om, j);
         if (j == lane) mine = Tj;
-        Tj = __fmul_rn(Tj, __fadd_rn(1.0f, -aj));
+        Tj = __fmul_rn(Tj, omj);
     }
     *t_end = Tj;
     return mine;
@@ -44,15 +45,18 @@ composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restr
     float T = 1.0f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_d = 0.f, acc_o = 0.f;
     int samples = n;
     int base = 0;
+    // the chunk being composited was loaded one iteration earlier: the loads of chunk k+1 are in flight while the 32-step
+    // transmittance chain of chunk k runs (the kernel's duration is the longest ray's chain, so latency per chunk is what counts)
+    float n_sig = 0.f, n_dl = 0.f, n_t = 0.f, n_r = 0.f, n_g = 0.f, n_b = 0.f;
+    if (lane < n) { const int64_t g = start + lane; n_sig = sigmas[g]; n_dl = deltas[g]; n_t = ts[g]; n_r = rgbs[3 * g]; n_g = rgbs[3 * g + 1]; n_b = rgbs[3 * g + 2]; }
     for (; base < n; base += 32) {
         const int s = base + lane;
         const bool valid = s < n;
         const int64_t g = start + s;
-        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        if (valid) {
-            a = alpha_of(sigmas[g], deltas[g]);
-            t = ts[g]; cr = rgbs[3 * g]; cg = rgbs[3 * g + 1]; cb = rgbs[3 * g + 2];
-        }
+        const float sig = n_sig, dl = n_dl, t = n_t, cr = n_r, cg = n_g, cb = n_b;
+        if (s + 32 < n) { const int64_t g2 = g + 32; n_sig = sigmas[g2]; n_dl = deltas[g2]; n_t = ts[g2]; n_r = rgbs[3 * g2]; n_g = rgbs[3 * g2 + 1]; n_b = rgbs[3 * g2 + 2]; }
+        else { n_sig = 0.f; n_dl = 0.f; n_t = 0.f; n_r = 0.f; n_g = 0.f; n_b = 0.f; }
+        const float a = valid ? alpha_of(sig, dl) : 0.f;
         float T_end;
         const float T_mine = chunk_transmittance(a, T, lane, &T_end);
         const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));
@@ -96,17 +100,21 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
     const float gO = dL_dopacity[ray], gD = dL_ddepth[ray];
     float T = 1.0f, cr_run = 0.f, cg_run = 0.f, cb_run = 0.f, d_run = 0.f, p_run = 0.f;
     int base = 0;
+    float n_sig = 0.f, n_dl = 0.f, n_t = 0.f, n_r = 0.f, n_g = 0.f, n_b = 0.f, n_gw = 0.f, n_ws = 0.f;   // next chunk, prefetched (see the forward kernel)
+    if (lane < n) {
+        const int64_t g = start + lane;
+        n_sig = sigmas[g]; n_dl = deltas[g]; n_t = ts[g]; n_r = rgbs[3 * g]; n_g = rgbs[3 * g + 1]; n_b = rgbs[3 * g + 2]; n_gw = dL_dws[g]; n_ws = ws[g];
+    }
     for (; base < n; base += 32) {
         const int s = base + lane;
         const bool valid = s < n;
         const int64_t g = start + s;
-        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dl = 0.f, gw = 0.f, wsv = 0.f;
-        if (valid) {
-            dl = deltas[g];
-            a = alpha_of(sigmas[g], dl);
-            t = ts[g]; cr = rgbs[3 * g]; cg = rgbs[3 * g + 1]; cb = rgbs[3 * g + 2];
-            gw = dL_dws[g]; wsv = ws[g];
-        }
+        const float sig = n_sig, dl = n_dl, t = n_t, cr = n_r, cg = n_g, cb = n_b, gw = n_gw, wsv = n_ws;
+        if (s + 32 < n) {
+            const int64_t g2 = g + 32;
+            n_sig = sigmas[g2]; n_dl = deltas[g2]; n_t = ts[g2]; n_r = rgbs[3 * g2]; n_g = rgbs[3 * g2 + 1]; n_b = rgbs[3 * g2 + 2]; n_gw = dL_dws[g2]; n_ws = ws[g2];
+        } else { n_sig = 0.f; n_dl = 0.f; n_t = 0.f; n_r = 0.f; n_g = 0.f; n_b = 0.f; n_gw = 0.f; n_ws = 0.f; }
+        const float a = valid ? alpha_of(sig, dl) : 0.f;
         float T_end;
         const float T_mine = chunk_transmittance(a, T, lane, &T_end);
         const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));

@@ -202,3 +202,33 @@ def test_device_side_render_equals_per_op_loop():
     assert int(a["total_samples"]) == int(b["total_samples"]) > 0
     for k in ("opacity", "depth", "rgb"):     # identical kernels and sample order: only the padded-row handling differs
         torch.testing.assert_close(a[k], b[k], rtol=0, atol=1e-6)
+
+
+def test_data_parallel_step_path_on_one_rank_group():
+    """the world_size > 1 code path (split graphs, gradient reduce-scatter + sharded Adam + all-gather of the fp16 shadow on a side
+    stream, overlapped with the next step's marching front) run on a 1-rank NCCL group: must reproduce the plain path"""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    rays = scenes.scene("lego", 256, seed=11)
+    o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
+    tgt = torch.rand(256, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    noise = torch.rand(256, device="cuda", generator=torch.Generator("cuda").manual_seed(6))
+    outs = []
+    for force in (False, True):
+        eng = _engine(256, force_dp_path=force)
+        eng.fixed_noise = noise
+        for s in range(1, 4):
+            eng.train_step(o, d, tgt, global_step=s)
+        eng.capture()
+        for s in range(4, 9):
+            eng.train_step(o, d, tgt, global_step=s)
+        p = eng.gather_master_params().clone()
+        torch.cuda.synchronize()
+        outs.append((p, eng.params_h.float().clone(), eng.loss_terms.clone()))
+    dist.destroy_process_group()
+    scale = outs[0][0].abs().max()
+    # same kernels in the same order; the hash-grid scatter uses float atomics -> tiny run-to-run differences only
+    assert (outs[0][0] - outs[1][0]).abs().max() <= 2e-3 * scale
+    assert (outs[0][1] - outs[1][1]).abs().max() <= 2e-3 * scale
+    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-2, atol=1e-5)
