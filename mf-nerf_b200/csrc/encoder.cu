@@ -189,16 +189,23 @@ grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_
     const int n_pad = (n + 15) & ~15;   // whole warps stay in the loop (shuffles below)
     const uint64_t pol_keep = umma::policy_evict_last();   // gradient table lines stay in L2 while the other levels / kernels stream
     const int step = (int)gridDim.x * (int)(blockDim.x >> 1);
-    for (int i = (int)blockIdx.x * (int)(blockDim.x >> 1) + (int)(threadIdx.x >> 1); i < n_pad; i += step) {
-        uint32_t raw = 0u;
-        if (i < n) raw = __ldg(dl + i);
+    // software pipeline: the gradient and the position of the NEXT sample of this lane pair are requested before the current one is
+    // processed (the kernel used to spend ~40% of its issue slots waiting on these two loads at the top of every iteration)
+    int i = (int)blockIdx.x * (int)(blockDim.x >> 1) + (int)(threadIdx.x >> 1);
+    uint32_t raw_n = 0u;
+    float4 p_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) { raw_n = __ldg(dl + i); p_n = __ldg(x01 + i); }
+    for (; i < n_pad; i += step) {
+        const uint32_t raw = raw_n;
+        const float4 p = p_n;
+        raw_n = 0u;
+        if (i + step < n) { raw_n = __ldg(dl + i + step); p_n = __ldg(x01 + i + step); }
         const bool live = (raw & 0x7fff7fffu) != 0u;          // either half non-zero
         const uint32_t live_mask = __ballot_sync(FULL, live);
         if (live_mask == 0) continue;
         uint32_t gx = 0, gy = 0, gz = 0;
         float v[4][2];   // corners (x = gx + xb, y = gy + (c & 1), z = gz + (c >> 1))
         if (live) {
-            const float4 p = __ldg(x01 + i);
             const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&raw));
             const float px = fmaf(p.x, s, 0.5f), py = fmaf(p.y, s, 0.5f), pz = fmaf(p.z, s, 0.5f);
             const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);

@@ -264,7 +264,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + kFwdX, kFT * 32 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + kFwdX, kFT * 32 * 2, pol_stream); bulk_commit(); }      // X is next written by the next tile
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -282,7 +282,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); }   // H is next written by rgb layer 1's epilogue
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -315,7 +315,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBC, smem + kFwdC, kFT * 32 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + kFwdC, kFT * 32 * 2, pol_stream); bulk_commit(); }   // X, H1 stores have read their tiles
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -347,7 +347,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); }
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -366,6 +366,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             }
         }
         phase ^= 1u;
+        if (MODE == 1 && tid == 0) bulk_wait_read0();   // the last stores (CAT, last hidden tile) have read shared memory: the next tile may overwrite it
         tc_fence_before();
         __syncthreads();   // TMEM and the tiles are free for the next tile
         MFN_TS(8);

@@ -191,7 +191,11 @@ march_scan_write_kernel(const float* __restrict__ rays_o, const float* __restric
     const int64_t r = first + warp;
     for (int w = 0; w < warp; ++w) start += (first + w < n_rays) ? counts[first + w] : 0;
     if (r >= n_rays) return;
-    const int n = counts[r];
+    int n = counts[r];
+    // a caller that sized the sample arrays below the worst case (n_rays * max_samples, what the reference allocates) gets the
+    // overflowing rays truncated CONSISTENTLY: rays_a and the counter never point past `capacity`
+    if (start >= capacity) { start = capacity; n = 0; }
+    else if (start + n > capacity) n = (int)(capacity - start);
     if (lane == 0) {
         int64_t* row = rays_a + 3 * r;
         row[0] = r; row[1] = start; row[2] = n;

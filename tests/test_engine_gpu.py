@@ -232,3 +232,31 @@ def test_data_parallel_step_path_on_one_rank_group():
     assert (outs[0][0] - outs[1][0]).abs().max() <= 2e-3 * scale
     assert (outs[0][1] - outs[1][1]).abs().max() <= 2e-3 * scale
     torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-2, atol=1e-5)
+
+
+def test_unbounded_scene_with_distortion_loss_trains_and_renders():
+    """BASELINE.json configs 4/5 in miniature: scale 16 (6 cascades, exp_step_factor 1/256: the multi-cascade, variable-dt marcher
+    paths), distortion loss on, T = 2^17; loss must go down and the device-side renderer must agree with the per-op loop"""
+    from mfnerf_b200.engine import NGPEngine
+    eng = NGPEngine(scale=16.0, n_rays=1024, sample_capacity=1024 * 320, log2_T=17, distortion_w=1e-3)     # capacity below the total: truncation path
+    assert eng.cascades == 6 and eng.esf == 1.0 / 256
+    grid = scenes.syn.lego_density_grid(16.0, 6)
+    eng.density_grid.copy_(torch.from_numpy(grid).cuda())
+    eng.repack_bitfield(0.5)
+    o, d, _, _ = scenes.syn.random_rays(1024, seed=21)
+    tgt = scenes.syn.analytic_render(o, d)
+    o = torch.from_numpy(o).cuda(); d = torch.from_numpy(d).cuda(); tgt = tgt.cuda().float()
+    losses = []
+    for s in range(1, 40):
+        eng.train_step(o, d, tgt, global_step=s)
+        if s in (1, 39):
+            losses.append(float(eng.loss_terms.sum()))
+    n = int(eng.counter[0])
+    assert 0 < n <= eng.cap
+    ra = eng.rays_a.cpu()
+    assert int((ra[:, 1] + ra[:, 2]).max()) <= eng.cap
+    assert all(map(lambda v: v == v, losses)) and losses[1] < losses[0]
+    a = eng.render(o, d)
+    b = eng.render_reference_loop(o, d)
+    assert int(a["total_samples"]) == int(b["total_samples"])
+    torch.testing.assert_close(a["rgb"], b["rgb"], rtol=0, atol=1e-6)

@@ -22,9 +22,14 @@ for r in rows:
         continue
     if r and r[0] == "Line No":
         hdr = r
+        ix0_samples = hdr.index("# Samples")
         continue
     if hdr is None or len(r) < len(hdr) // 2 or not r[0].strip():
         continue          # SASS rows have an empty line number; the source rows carry the roll-up
+    try:
+        int(r[ix0_samples] or 0)
+    except (ValueError, IndexError):
+        continue          # a source line whose quoting confused the CSV reader
     r[1] = fname[:14] + ": " + r[1].strip()
     recs.append(r)
 ix = {h: i for i, h in enumerate(hdr)}
