@@ -48,7 +48,7 @@ def _pad(n, m=8):
 class NGPEngine:
     def __init__(self, scale=0.5, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, n_rays=8192,
                  device="cuda", lr=1e-2, loss_scale=1024.0, distortion_w=0.0, lambda_opacity=1e-3, sample_capacity=None, seed=1337,
-                 exp_step_factor=None, T_threshold=1e-4, world_size=1, process_group=None, force_dp_path=False):
+                 exp_step_factor=None, T_threshold=1e-4, world_size=1, process_group=None, force_dp_path=False, pipelined=True):
         self.dev = torch.device(device)
         self.scale, self.n_rays = float(scale), int(n_rays)
         self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)                     # networks.py:26
@@ -58,7 +58,11 @@ class NGPEngine:
         self.lr, self.loss_scale, self.T_thr = lr, float(loss_scale), float(T_threshold)
         self.distortion_w, self.lambda_opacity = float(distortion_w), float(lambda_opacity)
         self.world_size, self.pg = world_size, process_group
-        self.dp = world_size > 1 or bool(force_dp_path)     # force_dp_path: run the data-parallel code path on a 1-rank group (tests)
+        # pipelined: the optimiser (and, data-parallel, the gradient exchange) of step t runs on a side stream while step t+1's
+        # parameter-independent front (batch copy, AABB, marching) is already under way -- same arithmetic, same order per datum.
+        # force_dp_path: run the collectives of the data-parallel path on a 1-rank group (tests)
+        self.collectives = world_size > 1 or bool(force_dp_path)
+        self.dp = self.collectives or bool(pipelined)
         entries, *_ = field_ops.grid_layout(self.cfg.grid)
         self.n_mlp1 = 64 * 32 + 16 * 64
         self.n_xyz = self.n_mlp1 + entries * F
@@ -133,6 +137,7 @@ class NGPEngine:
                 "density_grid": self.density_grid.clone()}
 
     def load_state_dict(self, sd):
+        self._wait_comm()
         self.params[:self.n_xyz].copy_(sd["xyz_encoder.params"]); self.params[self.off_rgb:self.off_rgb + self.n_rgb].copy_(sd["rgb_net.params"])
         self.params_h.copy_(self.params)
         if "density_bitfield" in sd:
@@ -144,6 +149,7 @@ class NGPEngine:
     @torch.no_grad()
     def field(self, xyzs, dirs):
         """NGP.forward (networks.py:134-155) without autograd: (n,3),(n,3) -> sigmas (n) f32, rgbs (n,3) f32"""
+        self._wait_comm()
         n = xyzs.shape[0]
         cfg = ctypes.byref(self.cfg)
         need = _lib.lib.mfn_field_workspace_bytes(cfg, n, 0)
@@ -158,6 +164,7 @@ class NGPEngine:
     @torch.no_grad()
     def density(self, xyz):
         """NGP.density (networks.py:96-110) for (n,3) world positions -> sigmas (n)"""
+        self._wait_comm()
         n = xyz.shape[0]
         need = _lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), n, 0)
         ws = self.field_ws
@@ -294,8 +301,10 @@ class NGPEngine:
         if global_step % 16 == 0:                                                            # train.py:165-168
             self.update_density_grid(warmup=global_step < 256)
         if self.dp:
-            return self._step_dp(lambda: (self.rays_o.copy_(rays_o, non_blocking=True), self.rays_d.copy_(rays_d, non_blocking=True),
-                                          self.target.copy_(target, non_blocking=True)) if rays_o is not None else None, lr, global_step)
+            self._step_dp(lambda: (self.rays_o.copy_(rays_o, non_blocking=True), self.rays_d.copy_(rays_d, non_blocking=True),
+                                   self.target.copy_(target, non_blocking=True)) if rays_o is not None else None, lr, global_step)
+            self._wait_comm()      # callers of train_step may read the parameters right away; train_step_packed leaves the optimiser in flight
+            return
         if rays_o is not None:
             self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
         self._run_forward_backward()
@@ -329,8 +338,8 @@ class NGPEngine:
         W = self.world_size
         assert self.n_params % (8 * W) == 0, "flat parameter vector is padded to a multiple of 8 * world_size"
         self._shard = self.n_params // W
-        self._rank = torch.distributed.get_rank(self.pg)
-        self._grad_shard = torch.zeros(self._shard, device=self.dev)
+        self._rank = torch.distributed.get_rank(self.pg) if self.collectives else 0
+        self._grad_shard = torch.zeros(self._shard, device=self.dev) if self.collectives else None
         self._comm_stream = torch.cuda.Stream(self.dev)
         self._bwd_done = torch.cuda.Event()
         self._comm_done = torch.cuda.Event()
@@ -368,6 +377,13 @@ class NGPEngine:
         r, n = self._rank, self._shard
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(self._bwd_done)
+            if not self.collectives:       # one GPU: only the optimiser is deferred
+                call("mfn_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
+                     float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1), ptr(self.overflow), 1,
+                     stream_ptr(self.dev))
+                self._comm_done.record(self._comm_stream)
+                self._comm_pending = True
+                return
             torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
             torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
             sl = slice(r * n, (r + 1) * n)
@@ -381,9 +397,9 @@ class NGPEngine:
 
     def gather_master_params(self):
         """world_size > 1: the fp32 master parameters are sharded over the ranks; returns the full vector (state_dict, tests)"""
-        if not self.dp:
-            return self.params
         self._wait_comm()
+        if not self.collectives:
+            return self.params
         torch.cuda.current_stream(self.dev).synchronize()
         full = torch.empty_like(self.params)
         r, n = self._rank, self._shard
@@ -416,6 +432,7 @@ class NGPEngine:
         """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples): the device-side
         wavefront of csrc/render.cu.  The host only looks at the alive count between batches of `iterations_per_batch` iterations."""
         d = self.dev
+        self._wait_comm()
         N = rays_o.shape[0]
         rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
         min_samples = (1 if self.esf == 0 else 4) if min_chunk is None else int(min_chunk)     # rendering.py:70
@@ -449,6 +466,7 @@ class NGPEngine:
         """render(test_time=True) (rendering.py:46-118) for (N,3) rays -> dict(rgb, depth, opacity, total_samples)"""
         import vren
         d = self.dev
+        self._wait_comm()
         N = rays_o.shape[0]
         _, hits_t, _ = vren.ray_aabb_intersect(rays_o, rays_d, self.center, self.half_size, 1)
         hits_t = hits_t[:, 0].contiguous()
