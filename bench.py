@@ -214,7 +214,7 @@ def run_ours(args):
         s = state["step"]
         eng.train_step_packed(pool[s % POOL], global_step=s)
         if i_host_loss is not None:
-            loss_host[i_host_loss].copy_(eng.loss_terms, non_blocking=True)
+            eng.loss_to_host(loss_host[i_host_loss])
         state["step"] = s + 1
 
     # ---- warm-up (eager first so that lazy initialisation happens outside capture), then capture

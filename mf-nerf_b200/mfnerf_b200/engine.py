@@ -311,6 +311,7 @@ class NGPEngine:
         self._optimizer_step(lr)
 
     def _run_forward_backward(self):
+        self._wait_loss_read()
         if self._graph is not None:
             self._graph.replay()
             self.graph_replays += 1
@@ -323,7 +324,7 @@ class NGPEngine:
         if global_step is None:
             global_step = self.step_count
         if self.dp:
-            return self._step_dp(lambda: self.rays.copy_(batch, non_blocking=True), lr, global_step)
+            return self._step_dp(lambda: self._load_batch(batch), lr, global_step)
         if global_step % 16 == 0:
             self.update_density_grid(warmup=global_step < 256)
         self.rays.copy_(batch, non_blocking=True)
@@ -344,6 +345,51 @@ class NGPEngine:
         self._bwd_done = torch.cuda.Event()
         self._comm_done = torch.cuda.Event()
         self._comm_pending = False
+
+    def _load_batch(self, batch):
+        """(3, R, 3) [rays_o | rays_d | target] -> self.rays.  A HOST batch (pinned memory) crosses PCIe on its own stream into a ring of
+        staging buffers -- the host runs ahead of the GPU, so the transfer of step t+k overlaps the kernels of step t -- and the main
+        stream only pays a device-to-device copy."""
+        if batch.is_cuda:
+            self.rays.copy_(batch, non_blocking=True)
+            return
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty_like(self.rays) for _ in range(4)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(4)]
+            self._stage_free = [torch.cuda.Event() for _ in range(4)]
+            self._h2d_stream = torch.cuda.Stream(self.dev)
+            self._stage_k = 0
+            for e in self._stage_free:
+                e.record(torch.cuda.current_stream(self.dev))
+        k = self._stage_k % 4
+        self._stage_k += 1
+        main = torch.cuda.current_stream(self.dev)
+        self._h2d_stream.wait_event(self._stage_free[k])
+        with torch.cuda.stream(self._h2d_stream):
+            self._stage[k].copy_(batch, non_blocking=True)
+            self._stage_ready[k].record(self._h2d_stream)
+        main.wait_event(self._stage_ready[k])
+        self.rays.copy_(self._stage[k], non_blocking=True)
+        self._stage_free[k].record(main)
+
+    def loss_to_host(self, dst_pinned):
+        """asynchronous read-back of the 3 loss terms of the step just enqueued into pinned host memory, on a side stream (the main
+        stream is not held up by the PCIe round trip; the next step's loss kernel waits for the read to be done)"""
+        if not hasattr(self, "_d2h_stream"):
+            self._d2h_stream = torch.cuda.Stream(self.dev)
+            self._loss_ready = torch.cuda.Event()
+            self._loss_read = torch.cuda.Event()
+        self._loss_ready.record(torch.cuda.current_stream(self.dev))
+        self._d2h_stream.wait_event(self._loss_ready)
+        with torch.cuda.stream(self._d2h_stream):
+            dst_pinned.copy_(self.loss_terms, non_blocking=True)
+            self._loss_read.record(self._d2h_stream)
+        self._loss_read_pending = True
+
+    def _wait_loss_read(self):
+        if getattr(self, "_loss_read_pending", False):
+            torch.cuda.current_stream(self.dev).wait_event(self._loss_read)
+            self._loss_read_pending = False
 
     def _wait_comm(self):
         if getattr(self, "_comm_pending", False):
@@ -366,11 +412,13 @@ class NGPEngine:
         if self._graph is not None:
             self._graph_march.replay()
             self._wait_comm()
+            self._wait_loss_read()
             self._graph.replay()
             self.graph_replays += 1
         else:
             self._march()
             self._wait_comm()
+            self._wait_loss_read()
             self._field_backward()
         self._bwd_done.record(main)
         self.step_count += 1

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert _lib.lib.mfn_version() == 100
-    assert _lib.lib.mfn_march_train_workspace_bytes(8192, 1024) == 8192 * 4 + 8192 * 1024 * 8
+    assert _lib.lib.mfn_march_train_workspace_bytes(8192, 1024) == 256 + 8192 * 4 + 8192 * 1024 * 8    # [queue header | counts | stash]
 
 
 def test_vren_dropin_surface():
@@ -37,3 +37,23 @@ def test_argument_errors_without_gpu():
     assert rc == -2 and b"bad argument" in _lib.lib.mfn_last_error()
     rc = _lib.lib.mfn_packbits(None, 7, 0, 0.0, None, None)
     assert rc == 0  # empty input is a no-op
+
+
+def test_render_and_field_entry_points_validate_arguments():
+    """the device-side render wavefront and the fused field ops reject bad arguments with MFN_ERR_ARG before touching CUDA"""
+    from mfnerf_b200 import _lib
+    from mfnerf_b200.engine import make_field_cfg
+    lib = _lib.lib
+    assert lib.mfn_render_workspace_bytes(640000, 1) >= 640000 * (8 + 8 + 4 + 48)   # hits_t, 2 alive lists, N_eff + 48 B per sample row
+    assert lib.mfn_render_workspace_bytes(-1, 1) == -1 and lib.mfn_render_workspace_bytes(10, 0) == -1
+    assert lib.mfn_render_begin(None, None, None, None, 16, 0.01, 1, None, None, None, None, 0, None) == -2
+    assert b"mfn_render_begin" in lib.mfn_last_error()
+    cfg = make_field_cfg(0.5)
+    assert lib.mfn_render_iterations(ctypes.byref(cfg), None, None, None, None, 16, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None) == -2
+    wide = make_field_cfg(0.5, rgb_channels=128)          # 128-wide rgb net: not covered by the fused kernels -> loud error, no silent fallback
+    rc = lib.mfn_render_iterations(ctypes.byref(wide), None, None, None, None, 16, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None)
+    assert rc == -2 and b"not covered" in lib.mfn_last_error()
+    assert lib.mfn_render_finish(None, None, None, 16, None) == -2
+    assert lib.mfn_render_iterations(ctypes.byref(cfg), None, None, None, None, 0, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None) == 0   # no rays: no-op
+    assert lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1 << 20, 1) >= (1 << 20) * 512     # 64 KiB activation blob per 128 samples
+    assert lib.mfn_field_fwd(ctypes.byref(cfg), None, None, None, None, 128, None, None, None, None, 0, None) == -2
