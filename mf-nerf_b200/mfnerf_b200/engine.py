@@ -341,7 +341,14 @@ class NGPEngine:
         self._shard = self.n_params // W
         self._rank = torch.distributed.get_rank(self.pg) if self.collectives else 0
         self._grad_shard = torch.zeros(self._shard, device=self.dev) if self.collectives else None
+        r, n = self._rank, self._shard
+        sl = slice(r * n, (r + 1) * n)
+        # static views / pointers of this rank's shard (the step loop is host-bound at several GPUs: no per-step slicing)
+        self._sl_ph = self.params_h[sl]
+        self._adam_ptrs = (ptr(self.params[sl]), ptr(self._grad_shard if self.collectives else self.grads), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]),
+                           ptr(self.params_h[sl]))
         self._comm_stream = torch.cuda.Stream(self.dev)
+        self._comm_stream_ptr = ctypes.c_void_p(self._comm_stream.cuda_stream)
         self._bwd_done = torch.cuda.Event()
         self._comm_done = torch.cuda.Event()
         self._comm_pending = False
@@ -422,25 +429,22 @@ class NGPEngine:
             self._field_backward()
         self._bwd_done.record(main)
         self.step_count += 1
-        r, n = self._rank, self._shard
-        with torch.cuda.stream(self._comm_stream):
-            self._comm_stream.wait_event(self._bwd_done)
-            if not self.collectives:       # one GPU: only the optimiser is deferred
-                call("mfn_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
-                     float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1), ptr(self.overflow), 1,
-                     stream_ptr(self.dev))
-                self._comm_done.record(self._comm_stream)
-                self._comm_pending = True
-                return
-            torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
-            torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
-            sl = slice(r * n, (r + 1) * n)
-            call("mfn_adam_step", ptr(self.params[sl]), ptr(self._grad_shard), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]), ptr(self.params_h[sl]), n,
-                 float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, self.world_size),
-                 ptr(self.overflow), 0, stream_ptr(self.dev))
-            self.grads.zero_()
-            torch.distributed.all_gather_into_tensor(self.params_h, self.params_h[sl], group=self.pg)
-            self._comm_done.record(self._comm_stream)
+        cs = self._comm_stream
+        cs.wait_event(self._bwd_done)
+        p_, g_, m_, v_, ph_ = self._adam_ptrs
+        lr_ = float(self.lr if lr is None else lr)
+        if not self.collectives:       # one GPU: only the optimiser is deferred
+            call("mfn_adam_step", p_, g_, m_, v_, ph_, self.n_params, lr_, 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1),
+                 ptr(self.overflow), 1, self._comm_stream_ptr)
+        else:
+            with torch.cuda.stream(cs):
+                torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+                call("mfn_adam_step", p_, g_, m_, v_, ph_, self._shard, lr_, 0.9, 0.999, 1e-15, self.step_count,
+                     mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 0, self._comm_stream_ptr)
+                self.grads.zero_()
+                torch.distributed.all_gather_into_tensor(self.params_h, self._sl_ph, group=self.pg)
+        self._comm_done.record(cs)
         self._comm_pending = True
 
     def gather_master_params(self):
