@@ -61,6 +61,22 @@ int mfn_packbits(const void* density_grid, int dtype, int64_t n_bytes, float den
 int mfn_packbits_dev_thr(const float* density_grid, int64_t n_bytes, float max_threshold, const float* threshold_dev,
                          uint8_t* density_bitfield, void* stream);
 
+/* ---- occupancy-grid update (NGP.update_density_grid, networks.py:157-197, 242-271) without host round trips ------------------------
+ * positions of grid cells with uniform jitter inside the cell, xyzs (n,3):  cell_indices != NULL -> those morton indices;
+ * random_cells != 0 -> n uniformly random cells (their morton indices go to indices_out); else cell i for i < n (all cells).
+ * cascade c covers [-s, s]^3 with s = min(2^(c-1), scale) (l.253-260).  Counter-based RNG keyed by `seed`. */
+int mfn_grid_cell_positions(const int32_t* cell_indices, int random_cells, int64_t n, int cascade, float scale, int grid_size, uint64_t seed,
+                            int32_t* indices_out, float* xyzs, void* stream);
+/* n draws from the occupied cells of one cascade (l.186-193), given the inclusive prefix count (int32, n_cells) of `grid > thr`:
+ * uniform k in [0, total) -> index of the k-th occupied cell.  With no occupied cell the draws are uniform over all cells. */
+int mfn_grid_draw_occupied(const int32_t* occupied_prefix_count, int64_t n_cells, int64_t n, uint64_t seed, int32_t* indices_out, void* stream);
+/* one cascade: grid = grid < 0 ? grid : max(grid * decay, sigma at the queried cells) (l.263-266).  cell_indices == NULL: all
+ * n == n_cells cells were queried in order; else `sigmas[i]` belongs to cell `cell_indices[i]`. */
+int mfn_grid_update(float* density_grid_cascade, const int32_t* cell_indices, const float* sigmas, int64_t n_cells, int64_t n, float decay,
+                    void* stream);
+/* *mean_out = mean of the cells > 0 (l.268), device to device; scratch16 = 16 zero-initialised bytes the call leaves zeroed */
+int mfn_grid_mean_positive(const float* density_grid, int64_t n, float* scratch16, float* mean_out, void* stream);
+
 /* ---- intersection ---------------------------------------------------------------------------------- */
 /* replaces vren.ray_aabb_intersect (binding.cpp:4-16 -> intersection.cu:59-100).
  * hit_cnt (n_rays) int32, hits_t (n_rays,max_hits,2) f32 (-1 = no hit), hits_voxel_idx (n_rays,max_hits) int64.

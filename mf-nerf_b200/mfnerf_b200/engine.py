@@ -178,40 +178,49 @@ class NGPEngine:
 
     @torch.no_grad()
     def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95):
-        """networks.py:242-271 without its host syncs (nonzero / .item()): occupied cells are drawn with a cumsum +
-        searchsorted instead of nonzero, and the packbits threshold min(mean, thr) is read on the device."""
-        d = self.dev
-        tmp = torch.zeros_like(self.density_grid)
-        M = G ** 3 // 4
+        """networks.py:242-271 without its host syncs (nonzero / .item()) and as a handful of fused kernels (csrc/density_grid.cu):
+        cells -> jittered positions -> density query -> decay/max update -> mean of the positive cells -> packbits with the threshold
+        min(mean, density_threshold) read on the device.  Occupied cells are drawn with a cumsum + searchsorted instead of nonzero."""
+        d, st = self.dev, stream_ptr(self.dev)
+        self._wait_comm()
+        G3 = G ** 3
+        M = G3 // 4
+        if not hasattr(self, "_dg_xyz"):
+            self._dg_xyz = torch.empty(G3, 3, device=d)                      # positions of the queried cells (all cells: G^3, sampled: 2M)
+            self._dg_idx = torch.empty(2 * M, dtype=torch.int32, device=d)
+            self._dg_sig = torch.empty(G3, device=d)
+            self._dg_scratch = torch.zeros(4, device=d)
+            self._dg_mean = torch.zeros(1, device=d)
+            self._dg_calls = 0
         for c in range(self.cascades):
+            self._dg_calls += 1
+            seed = (self._dg_calls * 0x9E3779B97F4A7C15 + 1337) & 0xFFFFFFFFFFFFFFFF     # same sequence on every rank: replicas stay identical
+            grid_c = self.density_grid[c]
             if warmup:                                    # get_all_cells (networks.py:157-168)
-                idx = None
-                coords = self.cell_coords
+                n, idx_ptr = G3, None
+                call("mfn_grid_cell_positions", None, 0, n, c, self.scale, G, seed, None, ptr(self._dg_xyz), st)
             else:                                         # sample_uniform_and_occupied_cells (networks.py:170-197)
-                coords1 = torch.randint(G, (M, 3), dtype=torch.int32, device=d)
-                idx1 = torch.empty(M, dtype=torch.int32, device=d)
-                call("mfn_morton3d", ptr(coords1), M, ptr(idx1), stream_ptr(d))
-                occ = (self.density_grid[c] > density_threshold)
-                cs = torch.cumsum(occ, 0, dtype=torch.int32)
-                k = (torch.rand(M, device=d) * cs[-1]).to(torch.int32)
-                idx2 = torch.searchsorted(cs, k, right=True).clamp_(max=G ** 3 - 1).to(torch.int32)
-                idx = torch.cat([idx1, idx2]).long()
-                coords = self.cell_coords[idx]
-            s = min(2.0 ** (c - 1), self.scale)
-            half = s / G
-            xyz = (coords.float() / (G - 1) * 2 - 1) * (s - half)
-            xyz += (torch.rand_like(xyz) * 2 - 1) * half
-            sig = self.density(xyz.contiguous())
-            if idx is None:
-                tmp[c] = sig
-            else:
-                tmp[c, idx] = sig
-        self.density_grid = torch.where(self.density_grid < 0, self.density_grid, torch.maximum(self.density_grid * decay, tmp))
-        pos = self.density_grid > 0
-        mean = (torch.where(pos, self.density_grid, torch.zeros_like(self.density_grid)).sum() / pos.sum().clamp_(min=1)).reshape(1).float()
-        self._mean_density = mean
-        call("mfn_packbits_dev_thr", ptr(self.density_grid), self.density_bitfield.numel(), float(density_threshold), ptr(mean),
-             ptr(self.density_bitfield), stream_ptr(d))
+                n, idx_ptr = 2 * M, ptr(self._dg_idx)
+                call("mfn_grid_cell_positions", None, 1, M, c, self.scale, G, seed, ptr(self._dg_idx), ptr(self._dg_xyz), st)
+                cs = torch.cumsum(grid_c > density_threshold, 0, dtype=torch.int32)
+                call("mfn_grid_draw_occupied", ptr(cs), G3, M, seed ^ 0x3333333333333333, ptr(self._dg_idx[M:]), st)
+                # morton-sorted cells are spatially coherent: the density query's hash-grid gathers run ~3x faster than on the raw draw
+                # (the update rule does not depend on the order of the cells)
+                self._dg_idx.copy_(torch.sort(self._dg_idx)[0])
+                call("mfn_grid_cell_positions", ptr(self._dg_idx), 0, 2 * M, c, self.scale, G, seed ^ 0x5555555555555555, None, ptr(self._dg_xyz), st)
+            sig = self._dg_sig[:n]
+            need = _lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), n, 0)
+            ws = self.field_ws
+            if need > ws.numel():
+                if self._cells_ws is None or self._cells_ws.numel() < need:
+                    self._cells_ws = torch.empty(need, dtype=torch.uint8, device=d)
+                ws = self._cells_ws
+            call("mfn_density_fwd", ctypes.byref(self.cfg), ptr(self.xyz_params_h), ptr(self._dg_xyz), n, None, ptr(sig), ptr(ws), ws.numel(), st)
+            call("mfn_grid_update", ptr(grid_c), idx_ptr, ptr(sig), G3, n, float(decay), st)
+        call("mfn_grid_mean_positive", ptr(self.density_grid), self.density_grid.numel(), ptr(self._dg_scratch), ptr(self._dg_mean), st)
+        self._mean_density = self._dg_mean
+        call("mfn_packbits_dev_thr", ptr(self.density_grid), self.density_bitfield.numel(), float(density_threshold), ptr(self._dg_mean),
+             ptr(self.density_bitfield), st)
 
     # ------------------------------------------------------------------------------------------------ training step
     def _forward_backward(self):
@@ -469,7 +478,7 @@ class NGPEngine:
         self._wait_comm()
         for k in ("params", "params_h", "exp_avg", "exp_avg_sq", "density_bitfield"):
             getattr(self, k).copy_(snap[k])          # in place: a captured graph holds these addresses
-        self.density_grid = snap["density_grid"].clone()
+        self.density_grid.copy_(snap["density_grid"])
         self.grads.zero_()
         self.step_count = snap["step_count"]
         torch.cuda.set_rng_state(snap["rng"], self.dev)

@@ -260,3 +260,52 @@ def test_unbounded_scene_with_distortion_loss_trains_and_renders():
     b = eng.render_reference_loop(o, d)
     assert int(a["total_samples"]) == int(b["total_samples"])
     torch.testing.assert_close(a["rgb"], b["rgb"], rtol=0, atol=1e-6)
+
+
+def test_update_density_grid_fused_kernels_follow_the_reference_rule():
+    """networks.py:242-271 semantics of csrc/density_grid.cu, checked with torch on the same queried positions: jittered positions
+    stay inside their cell, grid = where(grid < 0, grid, max(grid * decay, sigma)), occupied-cell draws hit occupied cells, the
+    bitfield is packbits(grid > min(mean of positive cells, threshold))"""
+    from mfnerf_b200.engine import G, MAX_SAMPLES
+    eng = _engine(64)
+    with torch.no_grad():
+        eng.params[:eng.n_mlp1] *= 4.0
+        eng.params[eng.n_mlp1:eng.n_xyz].uniform_(-0.5, 0.5)
+        eng.params_h.copy_(eng.params)
+    thr = 0.01 * MAX_SAMPLES / 3 ** 0.5
+    G3 = G ** 3
+    eng.density_grid[0, :1000] = -1.0                         # "invisible" cells must never change
+    for warm in (True, False):
+        old = eng.density_grid.clone()
+        eng.update_density_grid(warmup=warm)
+        torch.cuda.synchronize()
+        n = G3 if warm else G3 // 2
+        xyz = eng._dg_xyz[:n].clone()
+        idx = torch.arange(G3, device="cuda") if warm else eng._dg_idx[:n].long()
+        # (a) position -> cell: the inverse of xyzs_w = (coords / (G-1) * 2 - 1) * (s - half) +- half
+        s, half = 0.5, 0.5 / G
+        cell = torch.round(((xyz / (s - half)) + 1) / 2 * (G - 1))     # jitter is < half a cell spacing of this lattice
+        coords = eng.cell_coords[idx].float()
+        assert (xyz.abs() <= s).all()
+        assert ((xyz - (coords / (G - 1) * 2 - 1) * (s - half)).abs() <= half * 1.0001).all()
+        # (b) update rule on the very same positions
+        sig = eng.density(xyz)
+        tmp = torch.zeros(G3, device="cuda")
+        if warm:
+            tmp = sig
+        else:
+            tmp = tmp.scatter_reduce(0, idx, sig, reduce="amax", include_self=True)
+        want = torch.where(old[0] < 0, old[0], torch.maximum(old[0] * 0.95, tmp))
+        torch.testing.assert_close(eng.density_grid[0], want, rtol=1e-6, atol=1e-7)
+        assert (eng.density_grid[0, :1000] == -1.0).all()
+        if not warm:                                           # (c) half of the draws are occupied cells (the list is morton-sorted)
+            occ = old[0] > thr
+            if int(occ.sum()) > 0:
+                assert int(occ[idx].sum()) >= G3 // 4
+            assert 0 <= int(idx.min()) and int(idx.max()) < G3 and (idx[1:] >= idx[:-1]).all()
+        # (d) bitfield
+        pos = eng.density_grid > 0
+        mean = eng.density_grid[pos].mean()
+        torch.testing.assert_close(eng._mean_density[0], mean, rtol=1e-4, atol=0)
+        bits = scenes.syn.bitfield_from_grid((eng.density_grid.cpu().numpy()), float(min(float(eng._mean_density[0]), thr)))
+        assert (eng.density_bitfield.cpu().numpy() == bits).all()
