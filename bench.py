@@ -33,6 +33,7 @@ POOL = 64                      # distinct ray batches cycled through (64 x 8192 
 METRIC = "train_rays_per_sec"
 UNIT = "rays/s"
 WORKLOAD = "lego_synthetic_train_8192rays_scale0.5_hashL16F2T19"
+RENDER_MIN_CHUNK = 8           # lower bound of the per-iteration sample count of the test-time renderer (see engine.render)
 
 
 def parse():
@@ -333,20 +334,28 @@ def run_ours(args):
                             "peak_source": pk["src"], "launch_us": breakdown[top], "algorithmic_per_launch": work, "samples_per_launch": mean_s}
 
     # ---- 800x800 test-time render (second half of the metric), on the trained state
+    # ---- 800x800 test-time render (second half of the metric), on the trained state.  N > 1: every rank renders its tile of image rows
+    #      (mfnerf_b200.dist.tile_rows, no collective); a frame's time is its slowest rank's
     render = None
-    if rank == 0 and not args.no_render:
+    if not args.no_render:
+        from mfnerf_b200 import dist as mdist
         pose = syn.camera_poses(4, seed=7)
-        frames = []
+        row0, row1 = mdist.tile_rows(800, rank, world)
+        frames, out = [], None
         for k in range(4):
             o, d = syn.image_rays(pose[k])
-            o, d = torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)
-            torch.cuda.synchronize(dev)
+            o = torch.from_numpy(o.reshape(800, 800, 3)[row0:row1].reshape(-1, 3).copy()).to(dev)
+            d = torch.from_numpy(d.reshape(800, 800, 3)[row0:row1].reshape(-1, 3).copy()).to(dev)
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); out = eng.render(o, d); e1.record(); torch.cuda.synchronize(dev)
-            frames.append(e0.elapsed_time(e1))
+            e0.record(); out = eng.render(o, d, min_chunk=RENDER_MIN_CHUNK); e1.record(); torch.cuda.synchronize(dev)
+            frames.append(mdist.max_over_ranks(e0.elapsed_time(e1), dev, world))
         ms_frame = float(np.mean(frames[1:]))
-        render = {"fps_800x800": 1e3 / ms_frame, "ms_per_frame": ms_frame, "samples_per_ray": float(out["total_samples"]) / (800 * 800),
-                  "iterations": out.get("iterations"), "field_rows_per_ray": out.get("field_rows", 0) / (800 * 800)}
+        tot = mdist.sum_over_ranks(float(out["total_samples"]), dev, world)
+        rows = mdist.sum_over_ranks(float(out.get("field_rows", 0)), dev, world)
+        render = {"fps_800x800": 1e3 / ms_frame, "ms_per_frame": ms_frame, "samples_per_ray": tot / (800 * 800), "iterations": out.get("iterations"),
+                  "field_rows_per_ray": rows / (800 * 800), "tiles": f"{world} row tile(s), no collective",
+                  "schedule": f"N_samples = clamp(N_rays / N_alive, {RENDER_MIN_CHUNK}, 64) per iteration (reference: lower bound 1; same image, fewer iterations)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -16,8 +16,16 @@ eng.capture()
 for s in range(4, 300):
     eng.train_step_packed(pool[s % 8], global_step=s)
 torch.cuda.synchronize()
+pool_h = pool.cpu().pin_memory()
+loss_h = torch.zeros(400, 3).pin_memory()
+for s in range(300, 340):
+    eng.train_step_packed(pool_h[s % 8], global_step=s); eng.loss_to_host(loss_h[s - 300])
+torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
 pr = cProfile.Profile(); pr.enable()
-for s in range(300, 620):
-    eng.train_step_packed(pool[s % 8], global_step=s)
-pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+for s in range(340, 660):
+    eng.train_step_packed(pool_h[s % 8], global_step=s); eng.loss_to_host(loss_h[s - 340])
+pr.disable(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+print(f"host loop {(t1 - t0) / 320 * 1e3:.3f} ms/step, incl. drain {(t2 - t0) / 320 * 1e3:.3f} ms/step")
+pstats.Stats(pr).sort_stats("tottime").print_stats(22)
