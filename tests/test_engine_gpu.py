@@ -309,3 +309,31 @@ def test_update_density_grid_fused_kernels_follow_the_reference_rule():
         torch.testing.assert_close(eng._mean_density[0], mean, rtol=1e-4, atol=0)
         bits = scenes.syn.bitfield_from_grid((eng.density_grid.cpu().numpy()), float(min(float(eng._mean_density[0]), thr)))
         assert (eng.density_bitfield.cpu().numpy() == bits).all()
+
+
+@pytest.mark.parametrize("rgb_channels,rgb_layers", [(128, 2), (64, 1)])
+def test_other_rgb_net_shapes(rgb_channels, rgb_layers):
+    """the MF-NeRF scripts use --rgb_channels 128 (benchmarking/benchmark_llff_nerf_mf.sh): that shape runs on the unfused mma.sync
+    pipeline (field.cu), 64 x 1 on the fused kernels' one-hidden-layer instantiation; both must train and match the restatement"""
+    from oracle import field_ref as fr
+    eng = _engine(256, rgb_channels=rgb_channels, rgb_layers=rgb_layers)
+    rays = scenes.scene("lego", 256, seed=12)
+    o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
+    tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).cuda().float()
+    first = last = None
+    for s in range(1, 60):
+        eng.train_step(o, d, tgt, global_step=s)
+        if s == 1:
+            first = float(eng.loss_terms.sum())
+    last = float(eng.loss_terms.sum())
+    assert last < first
+    n = int(eng.counter[0])
+    p = eng.gather_master_params()
+    eng.params_h.copy_(p)
+    ref = fr.NGPRef(0.5, log2_T=15, rgb_channels=rgb_channels, rgb_layers=rgb_layers,
+                    params=(p[:eng.n_xyz].cpu(), p[eng.off_rgb:eng.off_rgb + eng.n_rgb].cpu())).cuda()
+    sig, rgb = eng.field(eng.xyzs[:n], eng.dirs[:n])
+    with torch.no_grad():
+        sig_r, rgb_r = ref(eng.xyzs[:n], eng.dirs[:n])
+    torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=2e-3)
+    torch.testing.assert_close(rgb, rgb_r, rtol=2e-2, atol=4e-3)
