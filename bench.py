@@ -243,7 +243,7 @@ def run_ours(args):
     def timed(pool, with_loss_readback):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         rewind()
-        eng.samples_acc.zero_()
+        eng.reset_samples_marched()
         l0 = _lib.lib.mfn_launch_count(); g0 = eng.graph_replays
         barrier()
         ev0.record()
@@ -259,7 +259,7 @@ def run_ours(args):
         if world > 1:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         launches = (_lib.lib.mfn_launch_count() - l0) + (eng.graph_replays - g0) * launches_per_fb
-        samples = float(eng.samples_acc.item())
+        samples = float(eng.samples_marched().item())
         if world > 1:
             t = torch.tensor([samples], device=dev, dtype=torch.float64); dist.all_reduce(t); samples = float(t.item())
         return ms, launches, samples

@@ -84,6 +84,12 @@ int mfn_grid_mean_positive(const float* density_grid, int64_t n, float* scratch1
 int mfn_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* half_sizes,
                            int64_t n_rays, int64_t n_voxels, int max_hits, int32_t* hit_cnt, float* hits_t,
                            int64_t* hits_voxel_idx, void* stream);
+/* engine front end of a training step in one launch: scene-box slab test with max_hits = 1 (rendering.py:27-28), near clamp
+ * (rendering.py:29) and the marcher's per-ray jitter (custom_functions.py:83 torch.rand_like), counter-based.  hits_t (n_rays,2);
+ * noise (n_rays) or NULL; call_counter: uint64 in device memory read (not written) by this call -- pass
+ * (char*)march_workspace + 16, which mfn_raymarching_train increments once per call, to get fresh jitter on every graph replay. */
+int mfn_ray_setup(const float* rays_o, const float* rays_d, const float* center_host, const float* half_size_host, int64_t n_rays,
+                  float near_distance, void* call_counter, float* hits_t, float* noise, void* stream);
 /* replaces vren.ray_sphere_intersect (binding.cpp:19-32 -> intersection.cu:156-197) */
 int mfn_ray_sphere_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* radii,
                              int64_t n_rays, int64_t n_spheres, int max_hits, int32_t* hit_cnt, float* hits_t,
@@ -93,7 +99,8 @@ int mfn_ray_sphere_intersect(const float* rays_o, const float* rays_d, const flo
 /* replaces vren.raymarching_train (binding.cpp:60-81 -> raymarching.cu:166-332), split so the caller can size
  * the sample arrays exactly: _count fills rays_a (n_rays,3) int64 and counter (2) int32 = {total samples,
  * n_rays}; _write then emits exactly the samples (rows < capacity).  mfn_raymarching_train = both in two launches; when
- * `capacity` is below the total it truncates the overflowing rays consistently (rays_a, counter[0] <= capacity). */
+ * `capacity` is below the total it truncates the overflowing rays consistently (rays_a, counter[0] <= capacity).
+ * Workspace header (first 256 bytes, zero it once): u32 @0 scratch, u64 @8 += samples marched by each call, u64 @16 += 1 per call. */
 int64_t mfn_march_train_workspace_bytes(int64_t n_rays, int max_samples);
 int mfn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* density_bitfield,
                           int cascades, float scale, float exp_step_factor, const float* noise, int grid_size, int max_samples,

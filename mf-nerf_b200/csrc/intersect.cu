@@ -105,6 +105,47 @@ static int launch_intersect(bool sphere, const float* o, const float* d, const f
     return check_launch(name, (cudaStream_t)stream);
 }
 
+namespace mfn {
+// Engine front end of a training step in ONE launch: ray / scene-box slab test with max_hits = 1 (rendering.py:27-28 ->
+// intersection.cu:5-22, 48-54), the near-plane clamp of rendering.py:29, and the per-ray jitter the reference draws with
+// torch.rand_like inside RayMarcher.forward (custom_functions.py:83).  The jitter is counter-based (splitmix64 of a device-side
+// call counter and the ray index), so a replayed CUDA graph draws fresh noise every step without a host-side generator.
+__global__ void ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float cx, float cy, float cz, float hx, float hy, float hz,
+                                 float near_distance, int64_t n_rays, unsigned long long* __restrict__ call_counter, float* __restrict__ hits_t,
+                                 float* __restrict__ noise) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long call = call_counter ? *call_counter : 0ull;   // only read here; bumped by mfn_raymarching_train
+    if (r < n_rays) {
+        const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+        const float ix = __fdiv_rn(1.0f, rays_d[3 * r]), iy = __fdiv_rn(1.0f, rays_d[3 * r + 1]), iz = __fdiv_rn(1.0f, rays_d[3 * r + 2]);
+        const float2 t = slab_test(ox, oy, oz, ix, iy, iz, cx, cy, cz, hx, hy, hz);
+        float t1 = -1.f, t2 = -1.f;
+        if (t.y > 0.f) {                       // (a miss is (-1, -1): fails this test too)
+            t1 = fmaxf(t.x, 0.f); t2 = t.y;
+            if (t1 >= 0.f && t1 < near_distance) t1 = near_distance;
+        }
+        hits_t[2 * r] = t1; hits_t[2 * r + 1] = t2;
+        if (noise && call_counter) {
+            unsigned long long x = (call + 1ull) * 0x9E3779B97F4A7C15ull ^ (unsigned long long)r * 0xD1342543DE82EF95ull;
+            x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; x ^= x >> 31;
+            noise[r] = (float)(x >> 40) * (1.0f / 16777216.0f);       // [0, 1), 24 random bits like torch.rand
+        }
+    }
+}
+}  // namespace mfn
+
+/* see include/mfnerf_b200.h */
+extern "C" int mfn_ray_setup(const float* rays_o, const float* rays_d, const float* center_host, const float* half_size_host, int64_t n_rays,
+                             float near_distance, void* call_counter, float* hits_t, float* noise, void* stream) {
+    if (n_rays < 0) { set_error("mfn_ray_setup: bad argument"); return MFN_ERR_ARG; }
+    if (n_rays == 0) return MFN_OK;
+    if (!rays_o || !rays_d || !center_host || !half_size_host || !hits_t) { set_error("mfn_ray_setup: null pointer"); return MFN_ERR_ARG; }
+    ray_setup_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, center_host[0], center_host[1], center_host[2],
+                                                                                  half_size_host[0], half_size_host[1], half_size_host[2], near_distance,
+                                                                                  n_rays, (unsigned long long*)call_counter, hits_t, noise);
+    return check_launch("mfn_ray_setup", (cudaStream_t)stream);
+}
+
 extern "C" int mfn_ray_aabb_intersect(const float* rays_o, const float* rays_d, const float* centers, const float* half_sizes,
                                       int64_t n_rays, int64_t n_voxels, int max_hits, int32_t* hit_cnt, float* hits_t,
                                       int64_t* hits_voxel_idx, void* stream) {

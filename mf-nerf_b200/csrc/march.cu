@@ -15,7 +15,7 @@ namespace mfn {
 
 constexpr int kMarchWarpsPerCta = 8;     // march_write: one warp per ray
 constexpr int kCountThreads = 128;
-constexpr int kWsHeader = 256;           // workspace: [header: ray queue counter][counts][stash]
+constexpr int kWsHeader = 256;           // workspace: [header: u32 ray queue | u64 @8 total samples | u64 @16 call counter][counts][stash]
 
 // Persistent groups with a dynamic ray queue: group g starts on ray g, and whenever its ray is finished it takes the next
 // unclaimed ray (one atomicAdd per ray).  A warp therefore never idles on its longest ray, which halves the number of batches
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kMarchWarpsPerCta * 32)
 march_scan_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const int32_t* __restrict__ counts,
                         const float2* __restrict__ stash, int max_samples, int64_t n_rays, int64_t capacity, int64_t* __restrict__ rays_a,
                         int32_t* __restrict__ counter, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-                        float* __restrict__ ts) {
+                        float* __restrict__ ts, unsigned long long* __restrict__ header) {
     __shared__ long long warp_sum[kMarchWarpsPerCta];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t first = (int64_t)blockIdx.x * kMarchWarpsPerCta;        // first ray of this CTA (a multiple of 8 -> 16-byte aligned counts)
@@ -199,7 +199,11 @@ march_scan_write_kernel(const float* __restrict__ rays_o, const float* __restric
     if (lane == 0) {
         int64_t* row = rays_a + 3 * r;
         row[0] = r; row[1] = start; row[2] = n;
-        if (r == n_rays - 1) { counter[0] = (int32_t)(start + n); counter[1] = (int32_t)n_rays; }
+        if (r == n_rays - 1) {
+            counter[0] = (int32_t)(start + n); counter[1] = (int32_t)n_rays;
+            header[1] += (unsigned long long)(start + n);     // running total of marched samples (statistics without an extra kernel)
+            header[2] += 1ull;                                // call counter: seeds the next mfn_ray_setup's jitter
+        }
     }
     if (n == 0) return;
     const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
@@ -294,7 +298,7 @@ static int march_count_impl(const float* rays_o, const float* rays_d, const floa
     if (blocks < 1) blocks = 1;
     {
         ProfScope ps("march_count", st);
-        cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);
+        if (K != 32 && K != 1) cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);     // the ray queue of the group variants
 #define MFN_MC(KK, A, B) march_count_kernel<KK, A, B><<<(unsigned)blocks, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, \
                                                                                   exp_step_factor, noise, max_samples, n_rays, counts, stash, queue)
 #define MFN_MCK(KK) { if (one && cdt) MFN_MC(KK, true, true); else if (one) MFN_MC(KK, true, false); else if (cdt) MFN_MC(KK, false, true); else MFN_MC(KK, false, false); }
@@ -360,7 +364,7 @@ extern "C" int mfn_raymarching_train(const float* rays_o, const float* rays_d, c
     const int blocks = (int)ceil_div(n_rays, kMarchWarpsPerCta);
     ProfScope ps("march_write", st);
     march_scan_write_kernel<<<blocks, kMarchWarpsPerCta * 32, 0, st>>>(rays_o, rays_d, counts, stash, max_samples, n_rays, capacity, rays_a, counter,
-                                                                       xyzs, dirs, deltas, ts);
+                                                                       xyzs, dirs, deltas, ts, (unsigned long long*)workspace);
     return check_launch("mfn_raymarching_train", st);
 }
 

@@ -112,15 +112,24 @@ class NGPEngine:
         self.dL_dsigmas, self.dL_drgbs, self.dL_dws = f(S), f(S, 3), torch.zeros(S, device=d)
         self.ws_incl, self.wts_incl = (f(S), f(S)) if self.distortion_w > 0 else (None, None)
         self.march_ws = torch.empty(_lib.lib.mfn_march_train_workspace_bytes(R, MAX_SAMPLES), dtype=torch.uint8, device=d)
+        self.march_ws[:256].zero_()                              # header: ray queue, running sample total (@8), call counter (@16)
+        self._march_hdr = self.march_ws[:256].view(torch.int64)  # [1] = samples marched so far, [2] = marcher calls
+        self._box = ((ctypes.c_float * 3)(0.0, 0.0, 0.0), (ctypes.c_float * 3)(self.scale, self.scale, self.scale))
         self.field_ws = torch.empty(_lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), S, 1), dtype=torch.uint8, device=d)
         self._graph = None
         self._cells_ws = None
         self.graph_replays = 0
         self.launches_per_forward_backward = 0
-        self.samples_acc = torch.zeros(1, dtype=torch.float64, device=d)   # running sum of marched samples (train/rm_s numerator)
         self.fixed_noise = None     # tests: jitter noise supplied by the caller instead of drawn per step
 
     # ------------------------------------------------------------------------------------------------ views
+    def samples_marched(self):
+        """running total of samples emitted by the training marcher (device int64 scalar; the reference's train/rm_s numerator)"""
+        return self._march_hdr[1]
+
+    def reset_samples_marched(self):
+        self._march_hdr[1].zero_()
+
     @property
     def xyz_params_h(self):
         return self.params_h[:self.n_xyz]
@@ -231,17 +240,15 @@ class NGPEngine:
     def _march(self):
         """parameter-independent front of the step: AABB, near clamp, jitter noise, ray marching (needs rays + bitfield only)"""
         d, st, R, S = self.dev, stream_ptr(self.dev), self.n_rays, self.cap
-        call("mfn_ray_aabb_intersect", ptr(self.rays_o), ptr(self.rays_d), ptr(self.center), ptr(self.half_size), R, 1, 1, ptr(self.hit_cnt),
-             ptr(self.hits_t), ptr(self.hits_idx), st)
-        call("mfn_clamp_near", ptr(self.hits_t), R, NEAR_DISTANCE, st)
-        if self.fixed_noise is None:
-            self.noise.uniform_(0, 1)                      # custom_functions.py:83
+        if self.fixed_noise is None:       # jitter drawn inside the front-end kernel (custom_functions.py:83)
+            call("mfn_ray_setup", ptr(self.rays_o), ptr(self.rays_d), self._box[0], self._box[1], R, NEAR_DISTANCE, ptr(self.march_ws[16:]), ptr(self.hits_t),
+                 ptr(self.noise), st)
         else:
+            call("mfn_ray_setup", ptr(self.rays_o), ptr(self.rays_d), self._box[0], self._box[1], R, NEAR_DISTANCE, None, ptr(self.hits_t), None, st)
             self.noise.copy_(self.fixed_noise)
         call("mfn_raymarching_train", ptr(self.rays_o), ptr(self.rays_d), ptr(self.hits_t), ptr(self.density_bitfield), self.cascades, self.scale,
              self.esf, ptr(self.noise), G, MAX_SAMPLES, R, S, ptr(self.rays_a), ptr(self.xyzs), ptr(self.dirs), ptr(self.deltas), ptr(self.ts),
              ptr(self.counter), ptr(self.march_ws), self.march_ws.numel(), st)
-        self.samples_acc.add_(self.counter[0])
 
     def _field_backward(self):
         """field forward, compositing, loss, and the whole backward pass into self.grads"""
