@@ -100,7 +100,7 @@ int mfn_ray_sphere_intersect(const float* rays_o, const float* rays_d, const flo
  * the sample arrays exactly: _count fills rays_a (n_rays,3) int64 and counter (2) int32 = {total samples,
  * n_rays}; _write then emits exactly the samples (rows < capacity).  mfn_raymarching_train = both in two launches; when
  * `capacity` is below the total it truncates the overflowing rays consistently (rays_a, counter[0] <= capacity).
- * Workspace header (first 256 bytes, zero it once): u32 @0 scratch, u64 @8 += samples marched by each call, u64 @16 += 1 per call. */
+ * Workspace header (first 256 bytes, zero it once): u64 @8 += samples marched by each call, u64 @16 += 1 per call. */
 int64_t mfn_march_train_workspace_bytes(int64_t n_rays, int max_samples);
 int mfn_march_train_count(const float* rays_o, const float* rays_d, const float* hits_t, const uint8_t* density_bitfield,
                           int cascades, float scale, float exp_step_factor, const float* noise, int grid_size, int max_samples,

@@ -1,67 +1,22 @@
 // raymarching_train / raymarching_test  (ref: models/csrc/raymarching.cu:166-332, 335-454)
 //
-// Train marcher = three launches, no atomics, deterministic layout (row i of rays_a is ray i and
-// start_idx is the exclusive prefix sum of N_samples -- a legal instance of the reference's
-// atomic-arrival order, raymarching.cu:237-241):
-//   1. march_count_kernel : one warp per ray, ballot compaction, stashes (t, dt) of every accepted sample
-//   2. scan_rays_kernel   : prefix sum of the per-ray counts -> rays_a (int64 triplets) + counter
-//   3. march_write_kernel : expands the stash into xyzs / dirs / deltas / ts (coalesced, exactly N rows)
+// Train marcher: no atomics, deterministic layout (row i of rays_a is ray i and start_idx is the exclusive
+// prefix sum of N_samples -- a legal instance of the reference's atomic-arrival order, raymarching.cu:237-241):
+//   1. march_count_warp_kernel : one warp per ray (march.cuh), stashes (t, dt) of every accepted sample
+//   2. march_scan_write_kernel : every CTA sums the counts in front of its rays, writes rays_a / counter and expands the
+//                                stash into xyzs / dirs / deltas / ts (coalesced, exactly N rows)       [mfn_raymarching_train]
+//      or scan_rays_kernel + march_write_kernel when the caller wants the count first            [mfn_march_train_count/_write]
 // Algorithmic bytes: 60 B/ray + 32 B/sample (+ 8 B/sample stash write+read, + C*G^3/8 B of bitfield).
 #include "march.cuh"
 #include "../../include/mfnerf_b200.h"
-#include <stdlib.h>
 
 namespace mfn {
 
 constexpr int kMarchWarpsPerCta = 8;     // march_write: one warp per ray
 constexpr int kCountThreads = 128;
-constexpr int kWsHeader = 256;           // workspace: [header: u32 ray queue | u64 @8 total samples | u64 @16 call counter][counts][stash]
+constexpr int kWsHeader = 256;           // workspace: [header: u64 @8 total samples | u64 @16 call counter][counts][stash]
 
-// Persistent groups with a dynamic ray queue: group g starts on ray g, and whenever its ray is finished it takes the next
-// unclaimed ray (one atomicAdd per ray).  A warp therefore never idles on its longest ray, which halves the number of batches
-// on the Lego-shaped workload (ray lengths vary 10x).  *queue must be 0 at launch (memset node in front of the kernel).
-template <int kMarchLanes, bool ONE_CASCADE, bool CONST_DT>
-__global__ void __launch_bounds__(kCountThreads)
-march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
-                   const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
-                   const float* __restrict__ noise, int max_samples, int64_t n_rays,
-                   int32_t* __restrict__ counts, float2* __restrict__ stash, unsigned int* __restrict__ queue) {
-    constexpr uint32_t FULL = 0xffffffffu;
-    constexpr int kCountGroupsPerCta = kCountThreads / kMarchLanes;
-    const int lane = threadIdx.x & 31, sub = lane & (kMarchLanes - 1), gbase = lane & ~(kMarchLanes - 1);
-    const int64_t n_groups = (int64_t)gridDim.x * kCountGroupsPerCta;
-    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
-    GroupState g;
-    g.alive = false; g.n = 0; g.t_base = 0.f; g.t2 = 0.f; g.pending = -INFINITY;
-    int64_t r = (int64_t)blockIdx.x * kCountGroupsPerCta + (threadIdx.x / kMarchLanes);   // first ray of this group
-    bool have = false;        // group-uniform: r is a ray in progress
-    bool exhausted = false;   // group-uniform: the queue has run dry
-    float2* my = stash;
-    while (true) {
-        if (!have && !exhausted) {     // pick up a ray (the first one is pre-assigned)
-            if (r >= n_rays) exhausted = true;
-            else {
-                const RayConst q = make_ray(rays_o, rays_d, r);
-                float t1 = hits_t[2 * r];
-                const float t2 = hits_t[2 * r + 1];
-                if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);  // only the first sample is jittered (l.195-198)
-                group_begin(g, q, t1, t2, max_samples);
-                my = stash + r * (int64_t)max_samples;
-                have = true;
-            }
-        }
-        if (!__any_sync(FULL, have)) break;
-        group_step<kMarchLanes, ONE_CASCADE, CONST_DT>(g, max_samples, c, bitfield, lane,
-                                                       [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); });
-        const bool done = have && !g.alive;   // ray done: publish its count and claim the next one
-        unsigned int nxt = 0;
-        if (done && sub == 0) { counts[r] = g.n; nxt = atomicAdd(queue, 1u); }
-        nxt = __shfl_sync(FULL, nxt, gbase);
-        if (done) { r = n_groups + (int64_t)nxt; have = false; }
-    }
-}
-
-// one warp per ray (MFN_MARCH_K=32, the default)
+// one warp per ray (march.cuh: march_ray_warp)
 template <bool ONE_CASCADE, bool CONST_DT>
 __global__ void __launch_bounds__(kCountThreads)
 march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
@@ -79,28 +34,6 @@ march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restric
     const int n = march_ray_warp<ONE_CASCADE, CONST_DT>(t1, t2, max_samples, q, c, bitfield, lane,
                                                         [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); });
     if (lane == 0) counts[r] = n;
-}
-
-// thread-per-ray variant (the reference's control flow): far fewer instructions (the DDA skip probes ~1/3 of the lattice points)
-// but one long dependent chain per ray; MFN_MARCH_K=1 selects it, LPW = active lanes per warp
-template <int LPW>
-__global__ void __launch_bounds__(32)
-march_count_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
-                          const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
-                          const float* __restrict__ noise, int max_samples, int64_t n_rays, int32_t* __restrict__ counts, float2* __restrict__ stash) {
-    if (threadIdx.x >= LPW) return;
-    const int64_t r = (int64_t)blockIdx.x * LPW + threadIdx.x;
-    if (r >= n_rays) return;
-    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
-    const RayConst q = make_ray(rays_o, rays_d, r);
-    float t1 = hits_t[2 * r];
-    const float t2 = hits_t[2 * r + 1];
-    if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);
-    float2* my = stash + r * (int64_t)max_samples;
-    float t_after;
-    int n = 0;
-    if (t1 >= 0.0f) n = march_ray_thread(t1, t2, max_samples, q, c, bitfield, [&](int k, float tk, float dt, float, float, float) { my[k] = make_float2(tk, dt); }, &t_after);
-    counts[r] = n;
 }
 
 constexpr int kScanThreads = 1024;
@@ -258,7 +191,7 @@ using namespace mfn;
 
 extern "C" int64_t mfn_march_train_workspace_bytes(int64_t n_rays, int max_samples) {
     if (n_rays < 0 || max_samples < 1) return -1;
-    // [header 256 B: ray queue][counts: n_rays int32, padded to 256 B][stash: n_rays * max_samples float2]
+    // [header 256 B: statistics][counts: n_rays int32, padded to 256 B][stash: n_rays * max_samples float2]
     const int64_t counts = ((n_rays * 4 + 255) / 256) * 256;
     return kWsHeader + counts + n_rays * (int64_t)max_samples * 8;
 }
@@ -281,44 +214,16 @@ static int march_count_impl(const float* rays_o, const float* rays_d, const floa
     if (n_rays == 0) { cudaMemsetAsync(counter, 0, 8, st); return check_launch("mfn_march_train_count", st); }
     if (!rays_o || !rays_d || !hits_t || !bitfield || !noise || !rays_a || !workspace) { set_error("mfn_march_train_count: null pointer"); return MFN_ERR_ARG; }
     if (workspace_bytes < mfn_march_train_workspace_bytes(n_rays, max_samples)) { set_error("mfn_march_train_count: workspace too small"); return MFN_ERR_ARG; }
-    unsigned int* queue = (unsigned int*)workspace;
     int32_t* counts = (int32_t*)((char*)workspace + kWsHeader);
     float2* stash = (float2*)((char*)workspace + kWsHeader + ((n_rays * 4 + 255) / 256) * 256);
-    // lanes per ray and rays per group are tunables (MFN_MARCH_K, MFN_MARCH_RPG); see DESIGN.md for the measured choice
-    static float rays_per_group = 0.f;
-    static int K = 0;
-    if (K == 0) {
-        const char* e = getenv("MFN_MARCH_RPG"); rays_per_group = e ? (float)atof(e) : 1.0f; if (!(rays_per_group >= 1.f)) rays_per_group = 1.f;
-        e = getenv("MFN_MARCH_K"); K = e ? atoi(e) : 32; if (K != 1 && K != 4 && K != 8 && K != 16 && K != 32) K = 32;
-    }
-    const int groups_per_cta = kCountThreads / (K > 1 ? K : 8);
-    int64_t blocks = (int64_t)((double)n_rays / (groups_per_cta * (double)rays_per_group) + 0.999);
-    const int64_t cap = (int64_t)kNumSMs * 14;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
     {
         ProfScope ps("march_count", st);
-        if (K != 32 && K != 1) cudaMemsetAsync(queue, 0, sizeof(unsigned int), st);     // the ray queue of the group variants
-#define MFN_MC(KK, A, B) march_count_kernel<KK, A, B><<<(unsigned)blocks, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, \
-                                                                                  exp_step_factor, noise, max_samples, n_rays, counts, stash, queue)
-#define MFN_MCK(KK) { if (one && cdt) MFN_MC(KK, true, true); else if (one) MFN_MC(KK, true, false); else if (cdt) MFN_MC(KK, false, true); else MFN_MC(KK, false, false); }
+        const unsigned wb = (unsigned)ceil_div(n_rays, kCountThreads / 32);
         const bool one = cascades == 1, cdt = exp_step_factor == 0.0f;
-        if (K == 1) {
-            static int lpw = 0;
-            if (lpw == 0) { const char* e2 = getenv("MFN_MARCH_LPW"); lpw = e2 ? atoi(e2) : 32; }
-            if (lpw == 8) march_count_thread_kernel<8><<<(unsigned)ceil_div(n_rays, 8), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
-            else if (lpw == 16) march_count_thread_kernel<16><<<(unsigned)ceil_div(n_rays, 16), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
-            else march_count_thread_kernel<32><<<(unsigned)ceil_div(n_rays, 32), 32, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, noise, max_samples, n_rays, counts, stash);
-        } else if (K == 4) MFN_MCK(4) else if (K == 8) MFN_MCK(8) else if (K == 16) MFN_MCK(16)
-        else {
-            const unsigned wb = (unsigned)ceil_div(n_rays, kCountThreads / 32);
 #define MFN_MW(A, B) march_count_warp_kernel<A, B><<<wb, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, \
                                                                                 noise, max_samples, n_rays, counts, stash)
-            if (one && cdt) MFN_MW(true, true); else if (one) MFN_MW(true, false); else if (cdt) MFN_MW(false, true); else MFN_MW(false, false);
+        if (one && cdt) MFN_MW(true, true); else if (one) MFN_MW(true, false); else if (cdt) MFN_MW(false, true); else MFN_MW(false, false);
 #undef MFN_MW
-        }
-#undef MFN_MCK
-#undef MFN_MC
     }
     if (with_scan) {
         note_launch(1);

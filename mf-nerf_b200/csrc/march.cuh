@@ -220,120 +220,6 @@ __device__ __forceinline__ int march_ray_warp(float t_start, float t2, int max_e
     return n;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Group marcher: K lanes (K = 4, 8, 16 or 32) walk one ray, so a warp carries 32/K rays.  Same scheme as the
-// warp marcher -- K consecutive lattice points probed at once, the reference's sequential visit order replayed
-// with (group-local) ballots -- but the work per batch is sized to the empty-space skip length (a skip jumps
-// ~5 lattice points at dt = sqrt(3)/1024 in a 128^3 grid).  The walk is split into a per-group state and a
-// one-batch step so that a group can pick up a new ray as soon as its own is done (march_count_kernel).
-// ---------------------------------------------------------------------------------------------------
-struct GroupState {
-    RayConst q;
-    float t_base, t2, pending;
-    int n;
-    bool alive;     // group-uniform: the ray still has lattice points to visit
-};
-
-__device__ __forceinline__ void group_begin(GroupState& g, const RayConst& q, float t_start, float t2, int max_emit) {
-    g.q = q; g.t_base = t_start; g.t2 = t2; g.pending = -INFINITY; g.n = 0;
-    g.alive = t_start >= 0.0f && t_start < t2 && 0 < max_emit;    // (ref loop condition, raymarching.cu:204)
-}
-
-// One batch of K lattice points for every group of the warp (all 32 lanes must call).  CONST_DT: exp_step_factor == 0, where
-// dt(t) = max(min(t*0, dt_max), dt_min) = dt_min for every finite t >= 0 (bit-identical, one FADD per lattice step).
-template <int K, bool ONE_CASCADE, bool CONST_DT, typename Emit>
-__device__ __forceinline__ void group_step(GroupState& g, int max_emit, const MarchConst& c, const uint8_t* __restrict__ bitfield, int lane, Emit emit) {
-    constexpr uint32_t FULL = 0xffffffffu;
-    constexpr uint32_t KM = (K == 32) ? 0xffffffffu : ((1u << K) - 1u);
-    const int sub = lane & (K - 1), gbase = lane & ~(K - 1);
-    // lattice: lane `sub` holds t_base advanced `sub` times
-    float my_t = g.t_base;
-#pragma unroll
-    for (int j = 0; j < K - 1; ++j) {
-        const float nx = CONST_DT ? __fadd_rn(c.dt_min, my_t) : march_next(my_t, c);
-        if (j < sub) my_t = nx;
-    }
-    const float t_next_base = __shfl_sync(FULL, CONST_DT ? __fadd_rn(c.dt_min, my_t) : march_next(my_t, c), gbase + K - 1);
-    const bool active = g.alive && my_t < g.t2;
-    Probe p;
-    p.occ = false; p.t_target = 0.f; p.dt = 0.f;
-    if (active) p = probe_cell<ONE_CASCADE>(my_t, g.q, c, bitfield);
-    const uint32_t act_mask = (__ballot_sync(FULL, active) >> gbase) & KM;
-    const uint32_t occ_mask = (__ballot_sync(FULL, active && p.occ) >> gbase) & KM;
-    const uint32_t pend_mask = (__ballot_sync(FULL, my_t >= g.pending) >> gbase) & KM;
-    int cur = 0;
-    if (g.pending > -INFINITY) {
-        cur = pend_mask ? (__ffs(pend_mask) - 1) : K;
-        if (cur < K) g.pending = -INFINITY;
-    }
-    // Where does the sequential marcher go after visiting THIS lattice point?  Computed by all lanes at once:
-    //   beyond t2     -> K+1 (the ray is finished when it lands here)
-    //   occupied      -> end of the run of consecutive occupied points (all of them are taken)
-    //   empty         -> first later point with t >= t_target (do { t += dt } while (t < t_target)), K = past this batch
-    unsigned long long hop;   // next index in bits 32.., points taken in bits 0..31 -- one (64-bit) shuffle per hop
-    {
-        int nx; uint32_t runbits = 0;
-        if (!active) nx = K + 1;
-        else if (p.occ) {
-            const uint32_t rest = (~(occ_mask >> sub)) & (KM >> sub);
-            const int run = rest ? (__ffs(rest) - 1) : (K - sub);
-            runbits = ((run >= 32) ? FULL : ((1u << run) - 1u)) << sub;
-            nx = sub + run;
-        } else nx = 0;   // filled in below
-        // binary search over the (ascending) lattice values of the group: smallest j in [sub+1, K) with t_j >= t_target, else K
-        int lo = sub + 1, hi = K;
-#pragma unroll
-        for (int it = 0; (1 << it) < K; ++it) {
-            const int mid = (lo + hi) >> 1;
-            const float tm = __shfl_sync(FULL, my_t, gbase + (mid < K ? mid : K - 1));
-            if (lo < hi) { if (tm >= p.t_target) hi = mid; else lo = mid + 1; }
-        }
-        if (active && !p.occ) nx = lo;
-        hop = ((unsigned long long)(uint32_t)nx << 32) | runbits;
-    }
-    uint32_t take = 0;
-    bool finished = false;
-    int exit_lane = -1;   // >= 0: the batch was left by a skip out of this (empty) lane -> its t_target carries over
-    while (true) {
-        const bool go = g.alive && !finished && cur < K;
-        if (!__any_sync(FULL, go)) break;
-        const unsigned long long h = __shfl_sync(FULL, hop, gbase + (cur < K ? cur : K - 1));
-        if (go) {
-            const int nx = (int)(h >> 32);
-            const uint32_t rb = (uint32_t)h;
-            if (nx > K) finished = true;
-            else {
-                take |= rb;
-                if (nx == K && !rb) exit_lane = cur;
-                cur = nx;
-            }
-        }
-    }
-    {
-        const float tg = __shfl_sync(FULL, p.t_target, gbase + (exit_lane >= 0 ? exit_lane : 0));
-        if (exit_lane >= 0) g.pending = tg;
-    }
-    int cnt = __popc(take);
-    if (g.alive && g.n + cnt >= max_emit) {   // sample budget reached inside this batch: keep the first ones only
-        const int keep = max_emit - g.n;
-        if (cnt > keep) {
-            uint32_t mm = take;
-            for (int i = 1; i < keep; ++i) mm &= mm - 1;
-            const int last = __ffs(mm) - 1;
-            take &= (last >= 31) ? FULL : ((1u << (last + 1)) - 1u);
-            cnt = keep;
-        }
-        finished = true;
-    }
-    if ((take >> sub) & 1u) emit(g.n + __popc(take & ((1u << sub) - 1u)), my_t, p.dt);
-    g.n += cnt;
-    if (finished) g.alive = false;
-    else if (g.alive) {
-        g.t_base = t_next_base;
-        g.alive = g.t_base >= 0.0f && g.t_base < g.t2 && g.n < max_emit;
-    }
-}
-
 // Sequential marcher (one thread per ray) -- the reference's own control flow; used by the test-time
 // marcher where each call only asks for a handful of samples per ray.
 template <typename Emit>
