@@ -4,6 +4,7 @@
 // zeroing of the gradient buffer for the next step.  HBM-bound: 30 B/param (p,g,m,v read; p,m,v,p16 written; g zeroed).
 #include "common.cuh"
 #include "umma.cuh"
+#include <stdlib.h>
 #include "../../include/mfnerf_b200.h"
 
 namespace mfn {
@@ -68,7 +69,9 @@ extern "C" int mfn_adam_step(float* params, float* grads, float* exp_avg, float*
     }
     const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     int64_t blocks = ceil_div(n / 4 + 1, 256);
-    const int64_t cap = (int64_t)kNumSMs * 8;
+    static int per_sm = 0;
+    if (per_sm == 0) { const char* e = getenv("MFN_ADAM_BPS"); per_sm = e ? atoi(e) : 32; if (per_sm < 1) per_sm = 32; }      // measured: 8 -> 75 us, 16 -> 64 us, 32 -> 63 us (11.4 M params)
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
     if (blocks > cap) blocks = cap;
     ProfScope ps("adam", (cudaStream_t)stream);
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_h, n, lr, beta1, beta2, eps, bc1,
