@@ -190,6 +190,9 @@ typedef struct mfn_field_cfg {
     float xyz_min[3], xyz_max[3];        /* scene box: x01 = (x - xyz_min) / (xyz_max - xyz_min) */
 } mfn_field_cfg;
 int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg_host, int64_t n_max, int training);
+/* 1 when this shape runs on the fused tcgen05 kernels (field_fused.cu), 0 when it runs on the unfused pipeline, <0 on a bad config.
+ * The fused backward reads nothing but the workspace, dL_dsigmas and dL_drgbs: `xyzs` may already be overwritten when it runs. */
+int mfn_field_is_fused(const mfn_field_cfg* cfg_host);
 /* xyzs, dirs (n,3) f32 -> sigmas (n) f32, rgbs (n,3) f32 (values rounded to fp16 like tcnn's output) */
 int mfn_field_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, const float* dirs,
                   int64_t n_max, const int32_t* n_dev, float* sigmas, float* rgbs, void* workspace, int64_t workspace_bytes, void* stream);

@@ -142,6 +142,11 @@ static inline unsigned ew_grid(int64_t n_max) {
 
 using namespace mfn;
 
+extern "C" int mfn_field_is_fused(const mfn_field_cfg* cfg) {
+    if (field_cfg_ok(cfg, "mfn_field_is_fused") != MFN_OK) return MFN_ERR_ARG;
+    return use_fused(cfg) ? 1 : 0;
+}
+
 extern "C" int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg, int64_t n_max, int training) {
     if (field_cfg_ok(cfg, "mfn_field_workspace_bytes") != MFN_OK || n_max < 0) return -1;
     const size_t v1 = field_ws(cfg, n_max, training != 0).total;

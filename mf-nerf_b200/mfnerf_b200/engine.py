@@ -63,6 +63,7 @@ class NGPEngine:
         # force_dp_path: run the collectives of the data-parallel path on a 1-rank group (tests)
         self.collectives = world_size > 1 or bool(force_dp_path)
         self.dp = self.collectives or bool(pipelined)
+        self._deep = False     # set in __init__ once the field config exists: next step's march may start before this step's backward
         entries, *_ = field_ops.grid_layout(self.cfg.grid)
         self.n_mlp1 = 64 * 32 + 16 * 64
         self.n_xyz = self.n_mlp1 + entries * F
@@ -97,6 +98,7 @@ class NGPEngine:
         self.noise = f(R)
         self.rays_a = torch.empty(R, 3, dtype=torch.int64, device=d)
         self.counter = torch.zeros(2, dtype=torch.int32, device=d)
+        self.n_field = torch.zeros(1, dtype=torch.int32, device=d)      # the field kernels' own copy of counter[0] (the next march overwrites counter)
         self.total_samples = torch.empty(R, dtype=torch.int64, device=d)
         self.opacity, self.depth, self.rgb, self.rgb_final = f(R), f(R), f(R, 3), f(R, 3)
         self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), torch.zeros(R, device=d), f(R, 3)
@@ -116,6 +118,9 @@ class NGPEngine:
         self._march_hdr = self.march_ws[:256].view(torch.int64)  # [1] = samples marched so far, [2] = marcher calls
         self._box = ((ctypes.c_float * 3)(0.0, 0.0, 0.0), (ctypes.c_float * 3)(self.scale, self.scale, self.scale))
         self.field_ws = torch.empty(_lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), S, 1), dtype=torch.uint8, device=d)
+        # fused field kernels: the backward pass reads only its workspace, so step t+1's marching front may overwrite the sample arrays
+        # as soon as step t's compositor backward is done and overlap step t's field backward + scatter
+        self._deep = self.dp and _lib.lib.mfn_field_is_fused(ctypes.byref(self.cfg)) == 1
         self._graph = None
         self._cells_ws = None
         self.graph_replays = 0
@@ -219,11 +224,9 @@ class NGPEngine:
                 call("mfn_grid_cell_positions", ptr(self._dg_idx), 0, 2 * M, c, self.scale, G, seed ^ 0x5555555555555555, None, ptr(self._dg_xyz), st)
             sig = self._dg_sig[:n]
             need = _lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), n, 0)
-            ws = self.field_ws
-            if need > ws.numel():
-                if self._cells_ws is None or self._cells_ws.numel() < need:
-                    self._cells_ws = torch.empty(need, dtype=torch.uint8, device=d)
-                ws = self._cells_ws
+            if getattr(self, "_dg_ws", None) is None or self._dg_ws.numel() < need:      # never the training workspace: the previous
+                self._dg_ws = torch.empty(need, dtype=torch.uint8, device=d)               # step's backward may still be reading it
+            ws = self._dg_ws
             call("mfn_density_fwd", ctypes.byref(self.cfg), ptr(self.xyz_params_h), ptr(self._dg_xyz), n, None, ptr(sig), ptr(ws), ws.numel(), st)
             call("mfn_grid_update", ptr(grid_c), idx_ptr, ptr(sig), G3, n, float(decay), st)
         call("mfn_grid_mean_positive", ptr(self.density_grid), self.density_grid.numel(), ptr(self._dg_scratch), ptr(self._dg_mean), st)
@@ -252,9 +255,15 @@ class NGPEngine:
 
     def _field_backward(self):
         """field forward, compositing, loss, and the whole backward pass into self.grads"""
+        self._field_front()
+        self._field_back()
+
+    def _field_front(self):
+        """field forward, compositing forward, loss, compositing backward: the last readers of the marcher's sample arrays"""
         d, st, R, S = self.dev, stream_ptr(self.dev), self.n_rays, self.cap
         cfg = ctypes.byref(self.cfg)
-        n_dev = ptr(self.counter)
+        self.n_field.copy_(self.counter[:1])
+        n_dev = ptr(self.n_field)
         call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), ptr(self.dirs), S, n_dev, ptr(self.sigmas),
              ptr(self.rgbs), ptr(self.field_ws), self.field_ws.numel(), st)
         call("mfn_composite_train_fw", ptr(self.sigmas), ptr(self.rgbs), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), self.T_thr, R, S,
@@ -273,6 +282,12 @@ class NGPEngine:
         call("mfn_composite_train_bw", ptr(self.dL_dopacity), ptr(self.dL_ddepth), ptr(self.dL_drgb), ptr(self.dL_dws), ptr(self.sigmas), ptr(self.rgbs),
              ptr(self.ws), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.opacity), ptr(self.depth), ptr(self.rgb), self.T_thr, R, S,
              ptr(self.dL_dsigmas), ptr(self.dL_drgbs), st)
+
+    def _field_back(self):
+        """field backward (MLP dgrad / wgrad, hash-grid scatter) into self.grads"""
+        st, S = stream_ptr(self.dev), self.cap
+        cfg = ctypes.byref(self.cfg)
+        n_dev = ptr(self.n_field)
         self.overflow.zero_()
         call("mfn_field_bwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
              self.loss_scale, ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
@@ -295,13 +310,15 @@ class NGPEngine:
         self.grads.zero_()
         l0 = _lib.lib.mfn_launch_count()
         if self.dp:
-            # two graphs: the marching front of step t+1 runs while step t's gradients are still being reduced (see _step_dp)
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            # three graphs, three stages of the step pipeline (see _step_dp)
+            ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
                 self._march()
             with torch.cuda.graph(gb):
-                self._field_backward()
-            self._graph_march, self._graph = ga, gb
+                self._field_front()
+            with torch.cuda.graph(gc):
+                self._field_back()
+            self._graph_march, self._graph, self._graph_back = ga, gb, gc
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -325,6 +342,14 @@ class NGPEngine:
             self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
         self._run_forward_backward()
         self._optimizer_step(lr)
+
+    def replay_forward_backward(self):
+        """replays everything capture() recorded, in order, on the current stream (tests; the training steps replay the pieces on
+        their own streams)"""
+        if self.dp:
+            self._graph_march.replay(); self._graph.replay(); self._graph_back.replay()
+        else:
+            self._graph.replay()
 
     def _run_forward_backward(self):
         self._wait_loss_read()
@@ -363,9 +388,11 @@ class NGPEngine:
         self._sl_ph = self.params_h[sl]
         self._adam_ptrs = (ptr(self.params[sl]), ptr(self._grad_shard if self.collectives else self.grads), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]),
                            ptr(self.params_h[sl]))
+        self._march_stream = torch.cuda.Stream(self.dev)
+        self._march_done = torch.cuda.Event()
+        self._cb_done = torch.cuda.Event()
         self._comm_stream = torch.cuda.Stream(self.dev)
         self._comm_stream_ptr = ctypes.c_void_p(self._comm_stream.cuda_stream)
-        self._bwd_done = torch.cuda.Event()
         self._comm_done = torch.cuda.Event()
         self._comm_pending = False
 
@@ -420,47 +447,61 @@ class NGPEngine:
             self._comm_pending = False
 
     def _step_dp(self, copy_batch, lr, global_step):
-        """one training step on world_size > 1.  The gradient exchange of step t (reduce-scatter, sharded Adam, all-gather) runs on
-        a side stream and is only waited for right before step t+1's field forward, so that step t+1's parameter-independent
-        marching front (and its host-to-device batch copy) overlap it."""
+        """One training step as a three-stage pipeline over three streams (same arithmetic, same order per datum as the plain path):
+          march stream : [occupancy update every 16 steps] -> batch copy -> AABB / jitter / ray marching of step t.  It starts as soon
+                         as step t-1's compositor backward has released the sample arrays and the ray batch (with the fused field
+                         kernels the backward pass reads only its workspace), so it overlaps step t-1's backward, scatter and Adam
+          main stream  : field forward, compositing, loss, compositing backward of step t            (CUDA graph)
+          back stream  : field backward + hash-grid scatter (CUDA graph), gradient exchange when data-parallel, Adam; only waited for
+                         right before step t+1's field forward."""
         if not hasattr(self, "_shard"):
             self._dp_setup()
         if global_step is None:
             global_step = self.step_count
         main = torch.cuda.current_stream(self.dev)
-        if global_step % 16 == 0:                       # the occupancy update queries the field: needs the updated parameters
-            self._wait_comm()
-            self.update_density_grid(warmup=global_step < 256)
-        copy_batch()
+        ms, cs = self._march_stream, self._comm_stream
+        ms.wait_stream(main)         # everything enqueued on the main stream so far: step t-1's field front, and whatever the caller did
+        with torch.cuda.stream(ms):
+            if not self._deep:
+                self._wait_comm()    # unfused field shapes: the backward still reads the sample arrays
+            if global_step % 16 == 0:                    # the occupancy update queries the field: needs the updated parameters
+                self._wait_comm()
+                self.update_density_grid(warmup=global_step < 256)
+            copy_batch()
+            if self._graph is not None:
+                self._graph_march.replay()
+            else:
+                self._march()
+            self._march_done.record(ms)
+        main.wait_event(self._march_done)
+        self._wait_comm()
+        self._wait_loss_read()
         if self._graph is not None:
-            self._graph_march.replay()
-            self._wait_comm()
-            self._wait_loss_read()
             self._graph.replay()
             self.graph_replays += 1
         else:
-            self._march()
-            self._wait_comm()
-            self._wait_loss_read()
-            self._field_backward()
-        self._bwd_done.record(main)
+            self._field_front()
+        self._cb_done.record(main)
         self.step_count += 1
-        cs = self._comm_stream
-        cs.wait_event(self._bwd_done)
+        cs.wait_event(self._cb_done)
         p_, g_, m_, v_, ph_ = self._adam_ptrs
         lr_ = float(self.lr if lr is None else lr)
-        if not self.collectives:       # one GPU: only the optimiser is deferred
-            call("mfn_adam_step", p_, g_, m_, v_, ph_, self.n_params, lr_, 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1),
-                 ptr(self.overflow), 1, self._comm_stream_ptr)
-        else:
-            with torch.cuda.stream(cs):
+        with torch.cuda.stream(cs):
+            if self._graph is not None:
+                self._graph_back.replay()
+            else:
+                self._field_back()
+            if not self.collectives:       # one GPU: the whole vector, gradient buffer zeroed by the optimiser
+                call("mfn_adam_step", p_, g_, m_, v_, ph_, self.n_params, lr_, 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1),
+                     ptr(self.overflow), 1, self._comm_stream_ptr)
+            else:
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
                 torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
                 call("mfn_adam_step", p_, g_, m_, v_, ph_, self._shard, lr_, 0.9, 0.999, 1e-15, self.step_count,
                      mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 0, self._comm_stream_ptr)
                 self.grads.zero_()
                 torch.distributed.all_gather_into_tensor(self.params_h, self._sl_ph, group=self.pg)
-        self._comm_done.record(cs)
+            self._comm_done.record(cs)
         self._comm_pending = True
 
     def gather_master_params(self):

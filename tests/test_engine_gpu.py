@@ -150,7 +150,7 @@ def test_graph_replay_equals_eager_and_training_reduces_loss():
     eng.grads.zero_(); eng._forward_backward(); torch.cuda.synchronize()
     g_eager = eng.grads.clone(); rgb_eager = eng.rgb_final.clone()
     eng.capture()
-    eng.grads.zero_(); eng._graph.replay(); torch.cuda.synchronize()
+    eng.grads.zero_(); eng.replay_forward_backward(); torch.cuda.synchronize()
     # identical launch sequence -> identical per-ray outputs; gradients differ only by atomic summation order
     assert torch.equal(eng.rgb_final, rgb_eager)
     torch.testing.assert_close(eng.grads, g_eager, rtol=1e-3, atol=1e-4 * g_eager.abs().max().item())
