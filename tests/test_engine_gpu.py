@@ -204,34 +204,40 @@ def test_device_side_render_equals_per_op_loop():
         torch.testing.assert_close(a[k], b[k], rtol=0, atol=1e-6)
 
 
-def test_data_parallel_step_path_on_one_rank_group():
-    """the world_size > 1 code path (split graphs, gradient reduce-scatter + sharded Adam + all-gather of the fp16 shadow on a side
-    stream, overlapped with the next step's marching front) run on a 1-rank NCCL group: must reproduce the plain path"""
+def test_pipelined_and_data_parallel_step_paths_reproduce_the_plain_path():
+    """three ways to run the same 12 training steps on the same batches with the same jitter:
+      plain      : everything on one stream, optimiser inside the step (pipelined=False)
+      pipelined  : train_step_packed -- three-stream pipeline, marching front of step t+1 overlapping backward / scatter / Adam of step t
+      data-par.  : the world_size > 1 code path (reduce-scatter + sharded Adam + all-gather of the fp16 shadow) on a 1-rank NCCL group
+    The kernels and their order per datum are the same, so the parameters must agree up to the float-atomic summation order."""
     import torch.distributed as dist
     if not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=torch.device("cuda", 0))
-    rays = scenes.scene("lego", 256, seed=11)
-    o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
-    tgt = torch.rand(256, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(5))
+    batches = []
+    for k in range(3):
+        rays = scenes.scene("lego", 256, seed=11 + k)
+        tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).float()
+        batches.append(torch.stack([torch.from_numpy(rays["rays_o"]), torch.from_numpy(rays["rays_d"]), tgt]).cuda().contiguous())
     noise = torch.rand(256, device="cuda", generator=torch.Generator("cuda").manual_seed(6))
     outs = []
-    for force in (False, True):
-        eng = _engine(256, force_dp_path=force)
+    for kw in (dict(pipelined=False), dict(pipelined=True), dict(force_dp_path=True)):
+        eng = _engine(256, **kw)
         eng.fixed_noise = noise
         for s in range(1, 4):
-            eng.train_step(o, d, tgt, global_step=s)
+            eng.train_step_packed(batches[s % 3], global_step=s)
         eng.capture()
-        for s in range(4, 9):
-            eng.train_step(o, d, tgt, global_step=s)
+        for s in range(4, 13):
+            eng.train_step_packed(batches[s % 3], global_step=s)          # no flush between steps: the optimiser stays in flight
         p = eng.gather_master_params().clone()
         torch.cuda.synchronize()
-        outs.append((p, eng.params_h.float().clone(), eng.loss_terms.clone()))
+        outs.append((p, eng.params_h.float().clone(), eng.loss_terms.clone(), int(eng.counter[0])))
     dist.destroy_process_group()
     scale = outs[0][0].abs().max()
-    # same kernels in the same order; the hash-grid scatter uses float atomics -> tiny run-to-run differences only
-    assert (outs[0][0] - outs[1][0]).abs().max() <= 2e-3 * scale
-    assert (outs[0][1] - outs[1][1]).abs().max() <= 2e-3 * scale
-    torch.testing.assert_close(outs[0][2], outs[1][2], rtol=1e-2, atol=1e-5)
+    for other in outs[1:]:
+        assert other[3] == outs[0][3]                                           # same samples marched in the last step
+        assert (outs[0][0] - other[0]).abs().max() <= 2e-3 * scale
+        assert (outs[0][1] - other[1]).abs().max() <= 2e-3 * scale
+        torch.testing.assert_close(outs[0][2], other[2], rtol=1e-2, atol=1e-5)
 
 
 def test_unbounded_scene_with_distortion_loss_trains_and_renders():
