@@ -391,6 +391,8 @@ class NGPEngine:
         self._march_stream = torch.cuda.Stream(self.dev)
         self._march_done = torch.cuda.Event()
         self._cb_done = torch.cuda.Event()
+        self._back_done = torch.cuda.Event()
+        self._back_pending = False
         self._comm_stream = torch.cuda.Stream(self.dev)
         self._comm_stream_ptr = ctypes.c_void_p(self._comm_stream.cuda_stream)
         self._comm_done = torch.cuda.Event()
@@ -461,6 +463,11 @@ class NGPEngine:
         main = torch.cuda.current_stream(self.dev)
         ms, cs = self._march_stream, self._comm_stream
         ms.wait_stream(main)         # everything enqueued on the main stream so far: step t-1's field front, and whatever the caller did
+        if self.collectives and self._back_pending:
+            # data-parallel: the gradient exchange leaves the SMs mostly idle, so the marching front is better spent overlapping IT
+            # than competing with the backward / scatter kernels for issue slots (measured on 8 GPUs: 0.478 vs 0.507 ms/step)
+            ms.wait_event(self._back_done)
+            self._back_pending = False
         with torch.cuda.stream(ms):
             if not self._deep:
                 self._wait_comm()    # unfused field shapes: the backward still reads the sample arrays
@@ -491,6 +498,8 @@ class NGPEngine:
                 self._graph_back.replay()
             else:
                 self._field_back()
+            if self.collectives:
+                self._back_done.record(cs); self._back_pending = True
             if not self.collectives:       # one GPU: the whole vector, gradient buffer zeroed by the optimiser
                 call("mfn_adam_step", p_, g_, m_, v_, ph_, self.n_params, lr_, 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1),
                      ptr(self.overflow), 1, self._comm_stream_ptr)
