@@ -213,8 +213,8 @@ int mfn_density_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, con
  * center_host / half_size_host / bg_rgb_host: 3 floats in HOST memory.  Needs the field shape the fused kernels cover. */
 int64_t mfn_render_workspace_bytes(int64_t n_rays, int min_samples);
 int mfn_render_begin(const float* rays_o, const float* rays_d, const float* center_host, const float* half_size_host, int64_t n_rays,
-                     float near_distance, int min_samples, float* opacity, float* depth, float* rgb, void* workspace, int64_t workspace_bytes,
-                     void* stream);
+                     float near_distance, int min_samples, int max_samples, float* opacity, float* depth, float* rgb, void* workspace,
+                     int64_t workspace_bytes, void* stream);
 int mfn_render_iterations(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* rays_o, const float* rays_d,
                           int64_t n_rays, const uint8_t* density_bitfield, int cascades, float scale, float exp_step_factor, int grid_size,
                           int max_samples, int min_samples, float T_threshold, int n_iterations, float* opacity, float* depth, float* rgb,

@@ -24,6 +24,7 @@ struct RenderPlan {
     int32_t spent;           // sum of N_samples so far (the reference's `samples`)
     int32_t iterations, rows_total_k;   // diagnostics: iterations run, field rows evaluated (in units of 1024)
     unsigned long long total_eff;   // sum of N_eff (the reference's total_samples)
+    unsigned int ticket;            // blocks of the compositor that have finished this iteration
 };
 
 constexpr int kPlanBytes = 256;
@@ -33,7 +34,7 @@ __global__ void render_begin_kernel(const float* __restrict__ rays_o, const floa
                                     float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb, RenderPlan* __restrict__ plan) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) {
-        plan->n_alive[0] = n_rays; plan->n_alive[1] = 0; plan->cur = 0; plan->n_samples = 0; plan->n_rows = 0; plan->spent = 0; plan->total_eff = 0ull; plan->iterations = 0; plan->rows_total_k = 0;
+        plan->n_alive[0] = n_rays; plan->n_alive[1] = 0; plan->cur = 0; plan->n_samples = 0; plan->n_rows = 0; plan->spent = 0; plan->total_eff = 0ull; plan->iterations = 0; plan->rows_total_k = 0; plan->ticket = 0u;
     }
     if (r >= n_rays) return;
     // ray / AABB slab test exactly as intersect.cu (ref: intersection.cu:5-22, 48-54)
@@ -54,8 +55,8 @@ __global__ void render_begin_kernel(const float* __restrict__ rays_o, const floa
     opacity[r] = 0.f; depth[r] = 0.f; rgb[3 * r] = 0.f; rgb[3 * r + 1] = 0.f; rgb[3 * r + 2] = 0.f;
 }
 
-// one thread: N_samples for this iteration, budget bookkeeping, reset of the list that the compositor is about to fill
-__global__ void render_plan_kernel(RenderPlan* __restrict__ plan, int n_rays, int min_samples, int max_samples, int cap_rows) {
+// one thread: N_samples for the coming iteration, budget bookkeeping, reset of the list that its compositor is going to fill
+__device__ void render_make_plan(RenderPlan* __restrict__ plan, int n_rays, int min_samples, int max_samples, int cap_rows) {
     const int cur = plan->cur;
     int na = plan->n_alive[cur];
     if (plan->spent >= max_samples) na = 0;                       // rendering.py:69  while samples < max_samples
@@ -70,6 +71,9 @@ __global__ void render_plan_kernel(RenderPlan* __restrict__ plan, int n_rays, in
     plan->n_rows = na * ns;
     plan->n_alive[cur ^ 1] = 0;
     if (na > 0) { plan->iterations += 1; plan->rows_total_k += (na * ns + 1023) / 1024; }
+}
+__global__ void render_plan_kernel(RenderPlan* __restrict__ plan, int n_rays, int min_samples, int max_samples, int cap_rows) {
+    render_make_plan(plan, n_rays, min_samples, max_samples, cap_rows);
 }
 
 __global__ void __launch_bounds__(128)
@@ -109,8 +113,12 @@ __device__ __forceinline__ float alpha_test(float sigma, float delta) { return _
 __global__ void __launch_bounds__(128)
 render_composite_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas, const float* __restrict__ ts,
                         int32_t* __restrict__ alive_lists, int list_stride, RenderPlan* __restrict__ plan, float T_thr, const int32_t* __restrict__ n_eff,
-                        float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb) {
-    const int cur = plan->cur, na = plan->n_alive[cur], ns = plan->n_samples;
+                        float* __restrict__ opacity, float* __restrict__ depth, float* __restrict__ rgb, int n_rays, int min_samples, int max_samples,
+                        int cap_rows) {
+    __shared__ int s_cur, s_na, s_ns;
+    if (threadIdx.x == 0) { s_cur = plan->cur; s_na = plan->n_alive[plan->cur]; s_ns = plan->n_samples; }   // read before the last block re-plans
+    __syncthreads();
+    const int cur = s_cur, na = s_na, ns = s_ns;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool keep = false;
@@ -149,9 +157,18 @@ render_composite_kernel(const float* __restrict__ sigmas, const float* __restric
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (keep) alive_lists[(cur ^ 1) * list_stride + base + __popc(km & ((1u << lane) - 1u))] = r;
+    // the last block to finish flips the lists and plans the next iteration (saves two single-thread launches per iteration)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&plan->ticket, 1u) == gridDim.x - 1) {
+            __threadfence();
+            plan->ticket = 0u;
+            plan->cur = cur ^ 1;
+            render_make_plan(plan, n_rays, min_samples, max_samples, cap_rows);
+        }
+    }
 }
-
-__global__ void render_flip_kernel(RenderPlan* __restrict__ plan) { plan->cur ^= 1; }
 
 __global__ void render_finish_kernel(float* __restrict__ rgb, const float* __restrict__ opacity, float bg_r, float bg_g, float bg_b, int n_rays) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,9 +207,9 @@ extern "C" int64_t mfn_render_workspace_bytes(int64_t n_rays, int min_samples) {
 }
 
 extern "C" int mfn_render_begin(const float* rays_o, const float* rays_d, const float* center_host, const float* half_size_host, int64_t n_rays,
-                                float near_distance, int min_samples, float* opacity, float* depth, float* rgb, void* workspace, int64_t workspace_bytes,
-                                void* stream) {
-    if (n_rays < 0 || n_rays > 0x3fffffff || min_samples < 1 || min_samples > 64) { set_error("mfn_render_begin: bad argument"); return MFN_ERR_ARG; }
+                                float near_distance, int min_samples, int max_samples, float* opacity, float* depth, float* rgb, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+    if (n_rays < 0 || n_rays > 0x3fffffff || min_samples < 1 || min_samples > 64 || max_samples < 1) { set_error("mfn_render_begin: bad argument"); return MFN_ERR_ARG; }
     if (n_rays == 0) return MFN_OK;
     const RenderWs w = render_ws(n_rays, min_samples);
     if (!rays_o || !rays_d || !center_host || !half_size_host || !opacity || !depth || !rgb || !workspace || (size_t)workspace_bytes < w.total) {
@@ -203,6 +220,8 @@ extern "C" int mfn_render_begin(const float* rays_o, const float* rays_d, const 
     render_begin_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, st>>>(rays_o, rays_d, center_host[0], center_host[1], center_host[2], half_size_host[0],
                                                                          half_size_host[1], half_size_host[2], near_distance, (int)n_rays, (float*)(ws + w.hits),
                                                                          (int32_t*)(ws + w.alive), opacity, depth, rgb, (RenderPlan*)(ws + w.plan));
+    render_plan_kernel<<<1, 1, 0, st>>>((RenderPlan*)(ws + w.plan), (int)n_rays, min_samples, max_samples, (int)w.cap_rows);   // plan of iteration 1
+    note_launch(1);
     return check_launch("mfn_render_begin", st);
 }
 
@@ -233,17 +252,16 @@ extern "C" int mfn_render_iterations(const mfn_field_cfg* cfg, const void* xyz_p
     f.w_sigma = (const __half*)xyz_params_h; f.table = f.w_sigma + 64 * 32 + 16 * 64; f.w_rgb = (const __half*)rgb_params_h; f.rgb_act = cfg->rgb_act;
     f.sigmas = (float*)(ws + w.sigmas); f.rgbs = (float*)(ws + w.rgbs);
     for (int it = 0; it < n_iterations; ++it) {
-        render_plan_kernel<<<1, 1, 0, st>>>(plan, (int)n_rays, min_samples, max_samples, (int)w.cap_rows);
         render_march_kernel<<<ray_blocks, 128, 0, st>>>(rays_o, rays_d, (float*)(ws + w.hits), (const int32_t*)(ws + w.alive), list_stride, plan, density_bitfield,
                                                         cascades, grid_size, scale, exp_step_factor, max_samples, (float*)(ws + w.xyzs), (float*)(ws + w.dirs),
                                                         (float*)(ws + w.deltas), (float*)(ws + w.ts), (int32_t*)(ws + w.neff));
-        note_launch(2);
+        note_launch(1);
         if ((rc = fused_field_forward(f, m, cfg->rgb_hidden, 0, st)) != MFN_OK) return rc;
         render_composite_kernel<<<ray_blocks, 128, 0, st>>>((const float*)(ws + w.sigmas), (const float*)(ws + w.rgbs), (const float*)(ws + w.deltas),
                                                             (const float*)(ws + w.ts), (int32_t*)(ws + w.alive), list_stride, plan, T_threshold,
-                                                            (const int32_t*)(ws + w.neff), opacity, depth, rgb);
-        render_flip_kernel<<<1, 1, 0, st>>>(plan);
-        note_launch(2);
+                                                            (const int32_t*)(ws + w.neff), opacity, depth, rgb, (int)n_rays, min_samples, max_samples,
+                                                            (int)w.cap_rows);
+        note_launch(1);
     }
     return check_launch("mfn_render_iterations", st);
 }

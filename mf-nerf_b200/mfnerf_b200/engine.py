@@ -562,7 +562,8 @@ class NGPEngine:
         opacity = torch.empty(N, device=d); depth = torch.empty(N, device=d); rgb = torch.empty(N, 3, device=d)
         center = (ctypes.c_float * 3)(0.0, 0.0, 0.0); half = (ctypes.c_float * 3)(self.scale, self.scale, self.scale)
         st = stream_ptr(d)
-        call("mfn_render_begin", ptr(rays_o), ptr(rays_d), center, half, N, NEAR_DISTANCE, min_samples, ptr(opacity), ptr(depth), ptr(rgb), ptr(ws), ws.numel(), st)
+        call("mfn_render_begin", ptr(rays_o), ptr(rays_d), center, half, N, NEAR_DISTANCE, min_samples, int(max_samples), ptr(opacity), ptr(depth), ptr(rgb), ptr(ws),
+             ws.numel(), st)
         cfg = ctypes.byref(self.cfg)
         done_evt = torch.cuda.Event()
         while True:
