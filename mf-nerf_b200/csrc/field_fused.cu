@@ -165,18 +165,22 @@ __device__ __forceinline__ float act_out(float x, int act) {
 }
 
 // TMEM (32 fp32 columns starting at col0) -> ReLU -> fp16 -> columns col0..col0+31 of row `row` of a [128 x 64] row-core tile
+// (16 columns per tcgen05.ld: the inference kernel lives on 48 registers to fit 5 CTAs per SM)
 __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* tile, int row, int col0) {
-    uint32_t r[32];
-    tmem_ld_x32(taddr + col0, r);
-    tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4 o;
-        o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
-        o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
-        o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
-        o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
-        *reinterpret_cast<uint4*>(tile + tile_off(row, col0 + c * 8, 64)) = o;
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[16];
+        tmem_ld_x16(taddr + col0 + 16 * h, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint4 o;
+            o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
+            o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
+            o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
+            o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
+            *reinterpret_cast<uint4*>(tile + tile_off(row, col0 + 16 * h + c * 8, 64)) = o;
+        }
     }
 }
 
@@ -190,8 +194,15 @@ constexpr int kFwdThreads = 256;
 #define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
 
 template <int NH2, int MODE>
-__global__ void __launch_bounds__(kFwdThreads, 4)
+__global__ void __launch_bounds__(kFwdThreads, MODE == 1 ? 4 : 5)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
+    // Inference / density modes keep no tile alive across stages, so X, H and CAT share ONE 16 KiB region and the 16-column output
+    // accumulator shares the hidden accumulator's TMEM columns: 36 KiB + 64 columns per CTA -> 5 CTAs / SM instead of 4 (the gather
+    // is bound by resident parallelism).  Training mode streams every tile to the blob and keeps the three regions apart.
+    constexpr bool ALIAS = (MODE != 1);
+    constexpr int oX = kFwdX, oH = ALIAS ? kFwdX : kFwdH, oC = ALIAS ? kFwdX : kFwdC;
+    constexpr int accO = ALIAS ? kAccH : kAccO;
+    constexpr int nCols = ALIAS ? 64 : kFwdCols;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -202,7 +213,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     if ((int64_t)blockIdx.x >= n_tiles) return;      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
     stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE != 2);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(&tmem_base_s, kFwdCols);
+    if (warp == 0) tmem_alloc(&tmem_base_s, nCols);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -236,23 +247,8 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
 #pragma unroll 2
             for (int l = 0; l < 16; ++l) {
                 const uint32_t v = gather_level_pair(table, m, l, x, y, z, xb, pol_keep);    // (invalid rows gather entry 0 harmlessly)
-                if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + kFwdX + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
+                if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + oX + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
             }
-        }
-        // ---- SH of the normalised direction -> CAT[:, 0:16]   (networks.py:145-146)
-        if (MODE != 2 && hsel == 0) {
-            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
-            if (valid) {
-                const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
-                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-                const float ux = (dx / nrm + 1.0f) / 2.0f, uy = (dy / nrm + 1.0f) / 2.0f, uz = (dz / nrm + 1.0f) / 2.0f;
-                float s[16];
-                sh4_eval(fmaf(ux, 2.f, -1.f), fmaf(uy, 2.f, -1.f), fmaf(uz, 2.f, -1.f), s);
-                o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
-                o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
-            }
-            *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 0, 32)) = o0;
-            *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 8, 32)) = o1;
         }
         MFN_TS(1); MFN_TS(109);
         fence_async_smem();
@@ -264,14 +260,14 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + kFwdX, kFT * 32 * 2, pol_stream); bulk_commit(); }      // X is next written by the next tile
+            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + oX, kFT * 32 * 2, pol_stream); bulk_commit(); }      // X is next written by the next tile
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
         MFN_TS(3);
         tc_fence_after();
-        relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
+        relu_epilogue32(trow + kAccH, smem + oH, row, 32 * hsel);
         MFN_TS(4);
         fence_async_smem();
         tc_fence_before();
@@ -282,15 +278,15 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
-            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); }   // H is next written by rgb layer 1's epilogue
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + accO, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); }   // H is next written by rgb layer 1's epilogue
             mma_commit(&bar);
         }
         if (hsel == 0) {
             mbar_wait(&bar, phase);
             tc_fence_after();
             uint32_t r[16];
-            tmem_ld_x16(trow + kAccO, r);
+            tmem_ld_x16(trow + accO, r);
             tmem_ld_wait();
             uint4 o0, o1;
             o0.x = pack2(__uint_as_float(r[0]), __uint_as_float(r[1])); o0.y = pack2(__uint_as_float(r[2]), __uint_as_float(r[3]));
@@ -299,9 +295,25 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
             if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
             if (MODE != 2) {
-                *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 16, 32)) = o0;
-                *reinterpret_cast<uint4*>(smem + kFwdC + tile_off(row, 24, 32)) = o1;
+                *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 16, 32)) = o0;
+                *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 24, 32)) = o1;
             }
+        } else if (MODE != 2) {
+            // the partner thread of the row meanwhile encodes the direction: SH of the normalised direction -> CAT[:, 0:16]
+            // (networks.py:145-146); CAT may overlay H1, which the layer-2 MMA has finished reading
+            mbar_wait(&bar, phase);
+            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+            if (valid) {
+                const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
+                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+                const float ux = (dx / nrm + 1.0f) / 2.0f, uy = (dy / nrm + 1.0f) / 2.0f, uz = (dz / nrm + 1.0f) / 2.0f;
+                float s[16];
+                sh4_eval(fmaf(ux, 2.f, -1.f), fmaf(uy, 2.f, -1.f), fmaf(uz, 2.f, -1.f), s);
+                o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
+                o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
+            }
+            *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 0, 32)) = o0;
+            *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 8, 32)) = o1;
         }
         phase ^= 1u;
         MFN_TS(6);
@@ -315,13 +327,13 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
-            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + kFwdC, kFT * 32 * 2, pol_stream); bulk_commit(); }   // X, H1 stores have read their tiles
+            for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + oC, kFT * 32 * 2, pol_stream); bulk_commit(); }   // X, H1 stores have read their tiles
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
         tc_fence_after();
-        relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
+        relu_epilogue32(trow + kAccH, smem + oH, row, 32 * hsel);
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -331,13 +343,13 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 tc_fence_after();
                 const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
-                for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
-                if (MODE == 1) { bulk_s2g_hint(blob + kBH2, smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+                for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
+                if (MODE == 1) { bulk_s2g_hint(blob + kBH2, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
                 mma_commit(&bar);
             }
             mbar_wait(&bar, phase); phase ^= 1u;
             tc_fence_after();
-            relu_epilogue32(trow + kAccH, smem + kFwdH, row, 32 * hsel);
+            relu_epilogue32(trow + kAccH, smem + oH, row, 32 * hsel);
             fence_async_smem();
             tc_fence_before();
             __syncthreads();
@@ -347,15 +359,15 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
-            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO, desc_kmajor(sbase + kFwdH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + kFwdH, kFT * 64 * 2, pol_stream); bulk_commit(); }
+            for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + accO, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
+            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); }
             mma_commit(&bar);
         }
         if (hsel == 0) {
             mbar_wait(&bar, phase);
             tc_fence_after();
             uint32_t r[8];
-            tmem_ld_x8(trow + kAccO, r);
+            tmem_ld_x8(trow + accO, r);
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
@@ -375,7 +387,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     if (MODE == 1 && tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, kFwdCols);
+    if (warp == 0) tmem_dealloc(tbase, nCols);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ backward
@@ -662,13 +674,15 @@ size_t fused_partial_bytes() { return (size_t)fused_bwd_max_ctas() * kNumWg * si
 
 template <int NH2, int MODE>
 static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
-    static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem), true);
+    constexpr int smem_bytes = (MODE == 1) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // inference / density: one shared tile region
+    constexpr int max_ctas = (MODE == 1) ? 4 : 5;
+    static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
     static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) { const char* e = getenv("MFN_FWD_CTAS"); ctas_per_sm = e ? atoi(e) : 4; if (ctas_per_sm < 1 || ctas_per_sm > 4) ctas_per_sm = 4; }
+    if (ctas_per_sm == 0) { const char* e = getenv("MFN_FWD_CTAS"); ctas_per_sm = e ? atoi(e) : max_ctas; if (ctas_per_sm < 1 || ctas_per_sm > max_ctas) ctas_per_sm = max_ctas; }
     const int64_t cap = ctas_per_sm * (int64_t)num_sms();
-    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, kFwdSmem, st>>>(a, m);
+    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(a, m);
 }
 
 // mode: 0 inference, 1 training, 2 density only
