@@ -190,16 +190,17 @@ __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* t
 // gather phase and the 64 accumulator columns in the hidden-layer epilogues.  In training mode every published tile is also sent
 // to the blob with one bulk async store (shared -> global) issued by thread 0.
 constexpr int kFwdThreads = 256;
+constexpr bool kTrainAlias = true;      // training mode too: one tile region, every bulk store waited for before its tile is overwritten
 // phase timestamps of CTA 0 (tools/fwd_phases.py): a.dbg != nullptr only in that tool
 #define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
 
 template <int NH2, int MODE>
-__global__ void __launch_bounds__(kFwdThreads, MODE == 1 ? 4 : 5)
+__global__ void __launch_bounds__(kFwdThreads, (MODE == 1 && !kTrainAlias) ? 4 : 5)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
     // Inference / density modes keep no tile alive across stages, so X, H and CAT share ONE 16 KiB region and the 16-column output
     // accumulator shares the hidden accumulator's TMEM columns: 36 KiB + 64 columns per CTA -> 5 CTAs / SM instead of 4 (the gather
     // is bound by resident parallelism).  Training mode streams every tile to the blob and keeps the three regions apart.
-    constexpr bool ALIAS = (MODE != 1);
+    constexpr bool ALIAS = (MODE != 1) || kTrainAlias;
     constexpr int oX = kFwdX, oH = ALIAS ? kFwdX : kFwdH, oC = ALIAS ? kFwdX : kFwdC;
     constexpr int accO = ALIAS ? kAccH : kAccO;
     constexpr int nCols = ALIAS ? 64 : kFwdCols;
@@ -261,7 +262,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + oX, kFT * 32 * 2, pol_stream); bulk_commit(); }      // X is next written by the next tile
+            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + oX, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: H1 overwrites X)
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -279,7 +280,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + accO, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); }   // H is next written by rgb layer 1's epilogue
+            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: CAT overwrites H1)
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -328,7 +329,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + oC, kFT * 32 * 2, pol_stream); bulk_commit(); }   // X, H1 stores have read their tiles
+            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + oC, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -674,8 +675,8 @@ size_t fused_partial_bytes() { return (size_t)fused_bwd_max_ctas() * kNumWg * si
 
 template <int NH2, int MODE>
 static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
-    constexpr int smem_bytes = (MODE == 1) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // inference / density: one shared tile region
-    constexpr int max_ctas = (MODE == 1) ? 4 : 5;
+    constexpr int smem_bytes = (MODE == 1 && !kTrainAlias) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // one shared tile region
+    constexpr int max_ctas = (MODE == 1 && !kTrainAlias) ? 4 : 5;
     static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
