@@ -17,16 +17,26 @@ constexpr int kCompWarps = 8;
 // alpha exactly as the reference computes it: 1 - __expf(-sigma*delta)  (volumerendering.cu:30)
 __device__ __forceinline__ float alpha_of(float sigma, float delta) { return __fadd_rn(1.0f, -__expf(-__fmul_rn(sigma, delta))); }
 
-// Sequential transmittance over one 32-sample chunk.  Returns T before this lane's sample; *t_end is T
-// after the whole chunk (identical in all lanes).
-__device__ __forceinline__ float chunk_transmittance(float a, float T_in, int lane, float* t_end) {
-    float Tj = T_in, mine = T_in;
-    const float om = __fadd_rn(1.0f, -a);      // (1 - a_j) is rounded once per sample, exactly as in the sequential loop
+// Sequential transmittance over one 32-sample chunk.  Returns T before this lane's sample; *t_end is T after the whole chunk
+// (identical in all lanes).  The 32 factors (1 - a_j) travel through shared memory: every lane reads them back as 8 independent
+// 16-byte loads and then runs the 32-step product without waiting on a shuffle per step (the shuffle version spent a third of the
+// kernel on short-scoreboard stalls; the kernel's duration is the longest ray's chain).
+__device__ __forceinline__ float chunk_transmittance(float a, float T_in, int lane, float* s_om, float* t_end) {
+    s_om[lane] = __fadd_rn(1.0f, -a);      // (1 - a_j) is rounded once per sample, exactly as in the sequential loop
+    __syncwarp();
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const float omj = __shfl_sync(0xffffffffu, om, j);
-        if (j == lane) mine = Tj;
-        Tj = __fmul_rn(Tj, omj);
+    for (int q = 0; q < 8; ++q) v[q] = reinterpret_cast<const float4*>(s_om)[q];
+    __syncwarp();                          // the next chunk may overwrite s_om
+    float Tj = T_in, mine = T_in;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float o[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (4 * q + k == lane) mine = Tj;
+            Tj = __fmul_rn(Tj, o[k]);
+        }
     }
     *t_end = Tj;
     return mine;
@@ -37,6 +47,7 @@ composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restr
                           const float* __restrict__ ts, const int64_t* __restrict__ rays_a, float T_thr, int64_t n_rows,
                           int64_t* __restrict__ total_samples, float* __restrict__ opacity, float* __restrict__ depth,
                           float* __restrict__ rgb, float* __restrict__ ws) {
+    __shared__ __align__(16) float s_om[kCompWarps][32];
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -58,7 +69,7 @@ composite_train_fw_kernel(const float* __restrict__ sigmas, const float* __restr
         else { n_sig = 0.f; n_dl = 0.f; n_t = 0.f; n_r = 0.f; n_g = 0.f; n_b = 0.f; }
         const float a = valid ? alpha_of(sig, dl) : 0.f;
         float T_end;
-        const float T_mine = chunk_transmittance(a, T, lane, &T_end);
+        const float T_mine = chunk_transmittance(a, T, lane, s_om[threadIdx.x >> 5], &T_end);
         const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));
         const uint32_t stop = __ballot_sync(0xffffffffu, valid && T_after <= T_thr);  // l.41
         const int last = stop ? (__ffs(stop) - 1) : 31;
@@ -85,6 +96,7 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
                           const int64_t* __restrict__ rays_a, const float* __restrict__ opacity, const float* __restrict__ depth,
                           const float* __restrict__ rgb, float T_thr, int64_t n_rows, float* __restrict__ dL_dsigmas,
                           float* __restrict__ dL_drgbs) {
+    __shared__ __align__(16) float s_om[kCompWarps][32];
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -116,7 +128,7 @@ composite_train_bw_kernel(const float* __restrict__ dL_dopacity, const float* __
         } else { n_sig = 0.f; n_dl = 0.f; n_t = 0.f; n_r = 0.f; n_g = 0.f; n_b = 0.f; n_gw = 0.f; n_ws = 0.f; }
         const float a = valid ? alpha_of(sig, dl) : 0.f;
         float T_end;
-        const float T_mine = chunk_transmittance(a, T, lane, &T_end);
+        const float T_mine = chunk_transmittance(a, T, lane, s_om[threadIdx.x >> 5], &T_end);
         const float T_after = __fmul_rn(T_mine, __fadd_rn(1.0f, -a));
         const uint32_t stop = __ballot_sync(0xffffffffu, valid && T_after <= T_thr);  // l.148
         const int last = stop ? (__ffs(stop) - 1) : 31;
