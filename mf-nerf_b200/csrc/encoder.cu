@@ -176,8 +176,34 @@ grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restri
 //   * same run aggregation over consecutive samples in the same cell (shuffle distances 2, 4, 8, 16 lanes).
 __global__ void __launch_bounds__(256)
 grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_t* __restrict__ n_dev, const uint32_t* __restrict__ dT, int64_t dT_stride,
-                         const __grid_constant__ GridMeta m, float* __restrict__ dgrid) {
+                         const __grid_constant__ GridMeta m, float* __restrict__ dgrid, const WgradReduce wr) {
     constexpr uint32_t FULL = 0xffffffffu;
+    if ((int)blockIdx.y == m.n_levels) {
+        // extra grid row: sums the MLP weight-gradient partials of field_bwd_fused (one per CTA) into the parameter gradient while the
+        // level rows scatter -- the two are independent, and a separate launch would sit on the step's critical path.
+        // 32 outputs x 8 slices of the partial list per pass, combined through shared memory.
+        __shared__ float sm[8][33];
+        const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5, n_out = wr.n_sigma + wr.n_rgb;
+        for (int j0 = blockIdx.x * 32; j0 < n_out; j0 += gridDim.x * 32) {
+            const int j = j0 + lane;
+            float s0 = 0.f, s1 = 0.f;
+            if (j < n_out) {
+                int c = slice;
+                for (; c + 8 < wr.n_parts; c += 16) { s0 += wr.partials[(size_t)c * wr.stride + j]; s1 += wr.partials[(size_t)(c + 8) * wr.stride + j]; }
+                if (c < wr.n_parts) s0 += wr.partials[(size_t)c * wr.stride + j];
+            }
+            sm[slice][lane] = s0 + s1;
+            __syncthreads();
+            if (slice == 0 && j < n_out) {
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += sm[k][lane];
+                if (j < wr.n_sigma) wr.d_sigma[j] += t; else wr.d_rgb[j - wr.n_sigma] += t;
+            }
+            __syncthreads();
+        }
+        return;
+    }
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int l = blockIdx.y;
     const int lane = threadIdx.x & 31, xb = lane & 1;
@@ -314,14 +340,14 @@ int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m
     return check_launch("mfn_grid_encode_fwd", st);
 }
 int grid_scatter_level_major(const float4* x01, int64_t n_max, const int32_t* n_dev, const __half* dT, int64_t dT_stride, const GridMeta& m, float* dgrid,
-                             cudaStream_t st) {
+                             const WgradReduce& wr, cudaStream_t st) {
     if (n_max <= 0) return MFN_OK;
     if (n_max > 0x7fffffff) { set_error("mfn_field_bwd: more than 2^31 samples"); return MFN_ERR_ARG; }
     static int per_sm = 0;
     if (per_sm == 0) { const char* e = getenv("MFN_SCATTER_BPS"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 2; }       // measured: 2 -> 174 us, 8 -> 178 us, 64 -> 235 us (per level)
-    dim3 grid(enc_grid(n_max, 128, per_sm), (unsigned)m.n_levels);
+    dim3 grid(enc_grid(n_max, 128, per_sm), (unsigned)m.n_levels + (wr.partials ? 1u : 0u));
     ProfScope ps("grid_encode_bwd", st);
-    grid_scatter_pair_kernel<<<grid, 256, 0, st>>>(x01, (int)n_max, n_dev, reinterpret_cast<const uint32_t*>(dT), dT_stride, m, dgrid);
+    grid_scatter_pair_kernel<<<grid, 256, 0, st>>>(x01, (int)n_max, n_dev, reinterpret_cast<const uint32_t*>(dT), dT_stride, m, dgrid, wr);
     return check_launch("mfn_grid_encode_bwd(level-major)", st);
 }
 int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F_, float* dgrid, int32_t* overflow_flag, cudaStream_t st) {

@@ -630,29 +630,6 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     if (warp == 0) tmem_dealloc(tbase, kBwdCols);
 }
 
-// d_params[j] += sum over CTAs of partials[c][j]; the first 3072 entries belong to the sigma net, the rest to the rgb net.
-// block = 32 outputs x 8 slices of the partial list (coalesced 128-byte rows, 8 independent accumulation chains per output)
-__global__ void __launch_bounds__(256)
-reduce_wgrad_kernel(const float* __restrict__ partials, int n_parts, int n_rgb, float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
-    __shared__ float sm[8][33];
-    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + lane;
-    float s0 = 0.f, s1 = 0.f;
-    if (j < 3072 + n_rgb) {
-        int c = slice;
-        for (; c + 8 < n_parts; c += 16) { s0 += partials[(size_t)c * kNumWg + j]; s1 += partials[(size_t)(c + 8) * kNumWg + j]; }
-        if (c < n_parts) s0 += partials[(size_t)c * kNumWg + j];
-    }
-    sm[slice][lane] = s0 + s1;
-    __syncthreads();
-    if (slice == 0 && j < 3072 + n_rgb) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][lane];
-        if (j < 3072) d_sigma[j] += t; else d_rgb[j - 3072] += t;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------ host side
 static int g_num_sms = 0;
 static int num_sms() {
@@ -705,20 +682,16 @@ static int launch_bwd(const FusedArgs& a, cudaStream_t st) {
     return (int)grid;
 }
 
-int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, cudaStream_t st) {
+int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, WgradReduce* wr, cudaStream_t st) {
     int grid;
     {
         ProfScope ps("field_bwd", st);
         grid = rgb_hidden == 2 ? launch_bwd<2>(a, st) : launch_bwd<1>(a, st);
     }
-    int rc = check_launch("mfn_field_bwd(fused)", st);
-    if (rc != MFN_OK) return rc;
-    const int n_rgb = 64 * 32 + (rgb_hidden - 1) * 64 * 64 + 16 * 64;
-    {
-        ProfScope ps("reduce_wgrad", st);
-        reduce_wgrad_kernel<<<(3072 + n_rgb + 31) / 32, 256, 0, st>>>(a.partials, grid, n_rgb, d_sigma_params, d_rgb_params);
-    }
-    return check_launch("mfn_field_bwd(reduce)", st);
+    wr->partials = a.partials; wr->n_parts = grid; wr->stride = kNumWg;
+    wr->n_sigma = 3072; wr->n_rgb = 64 * 32 + (rgb_hidden - 1) * 64 * 64 + 16 * 64;
+    wr->d_sigma = d_sigma_params; wr->d_rgb = d_rgb_params;
+    return check_launch("mfn_field_bwd(fused)", st);
 }
 
 }  // namespace mfn

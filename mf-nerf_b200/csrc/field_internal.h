@@ -46,9 +46,15 @@ struct EncArgs {
 };
 int grid_encode_forward(const EncArgs& e, const __half* table, const GridMeta& m, int F, __half* out, cudaStream_t st);
 // dT: level-major gradient [L][dT_stride] of half2 (F = 2), loss-scaled
+// per-CTA MLP weight-gradient partials of the fused backward kernel, reduced by an extra grid row of the scatter kernel
+struct WgradReduce {
+    const float* partials; int n_parts; int stride;   // partials[c * stride + j]
+    int n_sigma, n_rgb;                               // outputs: d_sigma[0 .. n_sigma), d_rgb[0 .. n_rgb)  (accumulated into)
+    float* d_sigma; float* d_rgb;
+};
 // x01: normalised positions (n,4) f32 (w unused)
 int grid_scatter_level_major(const float4* x01, int64_t n_max, const int32_t* n_dev, const __half* dT, int64_t dT_stride, const GridMeta& m, float* dgrid,
-                             cudaStream_t st);
+                             const WgradReduce& wr, cudaStream_t st);
 int grid_encode_backward(const EncArgs& e, const __half* dL_dout, const GridMeta& m, int F, float* dgrid, int32_t* overflow_flag, cudaStream_t st);
 
 // ---- fused tcgen05 field kernels (field_fused.cu) ----
@@ -76,6 +82,7 @@ bool fused_field_supported(const mfn_field_cfg* c);
 size_t fused_blob_bytes(int64_t n_max);
 size_t fused_partial_bytes();
 int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st);   // mode 0 inference, 1 training, 2 density
-int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, cudaStream_t st);
+// launches the backward kernel; the reduction of its per-CTA weight-gradient partials is described in *wr for the scatter kernel to do
+int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, WgradReduce* wr, cudaStream_t st);
 
 }  // namespace mfn

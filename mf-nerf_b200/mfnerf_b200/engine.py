@@ -393,7 +393,9 @@ class NGPEngine:
         self._cb_done = torch.cuda.Event()
         self._back_done = torch.cuda.Event()
         self._back_pending = False
-        self._comm_stream = torch.cuda.Stream(self.dev)
+        # high priority: the back stream (field backward, scatter, Adam) is the step's critical path; the marching front that overlaps it
+        # (default priority) only gets the issue slots it leaves free
+        self._comm_stream = torch.cuda.Stream(self.dev, priority=-1)
         self._comm_stream_ptr = ctypes.c_void_p(self._comm_stream.cuda_stream)
         self._comm_done = torch.cuda.Event()
         self._comm_pending = False
