@@ -4,18 +4,22 @@
 // rgb net with 1 or 2 hidden layers), the v1 pipeline of field.cu (encoder kernel -> mma.sync MLP kernels with every
 // intermediate in HBM).  Semantics: models/networks.py:96-155 (NGP.density / NGP.forward), TruncExp custom_functions.py:162-173.
 //
-// Forward, one CTA = 128 samples (thread t owns sample row t == TMEM lane t), persistent over tiles, 4 CTAs / SM:
-//   gather 16 levels x 8 corners (fp32 interpolation) -> X tile [128x32] fp16 in shared memory (canonical un-swizzled core-matrix
-//   layout, umma.cuh) -> tcgen05.mma X.W1^T -> TMEM -> ReLU -> H1 tile -> mma H1.W2^T -> h (16) -> sigma = exp(h0);
+// Forward, one CTA = 128 samples, 256 threads (two threads per sample row; row r == TMEM lane r), persistent over tiles, 5 CTAs / SM:
+//   gather 16 levels x 8 corners (lane pairs, fp32 interpolation) -> X tile [128x32] fp16 in shared memory (canonical un-swizzled
+//   core-matrix layout, umma.cuh) -> tcgen05.mma X.W1^T -> TMEM -> ReLU -> H1 tile -> mma H1.W2^T -> h (16) -> sigma = exp(h0);
 //   CAT tile = [SH4(dir) | h] -> mma CAT.W3^T -> ReLU -> mma .W4^T -> ReLU -> mma .W5^T -> sigmoid -> rgb.
+//   X, H and CAT live one after the other in ONE 16 KiB region and the two accumulators share 64 TMEM columns (36 KiB of shared
+//   memory and 48 registers per thread are what lets 5 CTAs share an SM; the gather is bound by resident parallelism).
 //   Nothing but xyz/dir in and sigma/rgb out touches HBM at inference.  In training the five activation tiles are also stored,
-//   as one contiguous 64 KiB blob per tile *in the shared-memory layout*, so that the backward kernel fetches a tile with a single
-//   bulk async copy (cp.async.bulk, the 1-D TMA path) and feeds it to the tensor cores without any re-staging.
-// Backward, one CTA = 128 samples, persistent, 2 CTAs / SM:
+//   as one contiguous 64 KiB blob per tile *in the shared-memory layout*, each with one bulk async store (shared -> global, waited
+//   for before the region is overwritten), so that the backward kernel fetches a tile with a single bulk async copy
+//   (cp.async.bulk, the 1-D TMA path) and feeds it to the tensor cores without any re-staging.
+// Backward, one CTA = 128 samples, 256 threads, persistent, 2 CTAs / SM (88 KiB of shared memory, 256 TMEM columns):
 //   dZ5 = dL/drgb * sigmoid' -> [dgrad mma -> TMEM -> ReLU mask -> dZ tile (in place of the activation it masks)] x 4 -> dX;
 //   the weight gradients dW = dZ^T.A are tcgen05 MMAs with M = 64, both operands read MN-major from the very same tiles, and
-//   they ACCUMULATE IN TMEM across all tiles of the CTA (fp32); one partial per CTA is written at the end and a small kernel reduces
-//   the partials (deterministic, no atomics).  dX (fp16, loss-scaled) goes to the hash-grid scatter kernel (encoder.cu).
+//   they ACCUMULATE IN TMEM across all tiles of the CTA (fp32); one partial per CTA is written at the end and an extra grid row of
+//   the scatter kernel (encoder.cu) sums the partials (deterministic, no atomics).  dX (fp16, loss-scaled, level-major) goes to the
+//   hash-grid scatter kernel.
 #include "field_internal.h"
 #include "grid_common.cuh"
 #include "sh4.cuh"

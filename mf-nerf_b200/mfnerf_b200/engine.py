@@ -1,11 +1,13 @@
 """Sync-free training / rendering engine: the reference's `training_step` (train.py:164-190) and
 `render(test_time=True)` (rendering.py:46-118) driven directly through the C ABI, without autograd and without
-host synchronisation inside a step, so the whole step can be replayed as one CUDA graph.
+host synchronisation inside a step.
 
-Step = [AABB + near clamp] -> march (count / scan / write) -> field fwd -> composite fw -> loss (+ distortion)
-       -> composite bw -> field bwd -> [all-reduce of the flat gradient when world_size > 1] -> fused Adam,
-with `update_density_grid` (networks.py:242-271) every 16 steps.  Sample arrays live in fixed-capacity buffers and every
-kernel reads the live sample count from device memory.
+Step = [occupancy update every 16 steps] -> AABB + near clamp + jitter -> march -> field fwd -> composite fw -> loss (+ distortion)
+       -> composite bw -> field bwd + hash-grid scatter -> [gradient exchange when world_size > 1] -> fused Adam.
+Sample arrays live in fixed-capacity buffers and every kernel reads the live sample count from device memory, so the step is
+three CUDA graphs (marching front | field front | field back) replayed on three streams as a pipeline: the marching front of step
+t+1 overlaps the field backward, scatter and optimiser of step t (`_step_dp`).  `pipelined=False` runs the same kernels on one
+stream (tests compare the two).  Rendering is the device-side wavefront of csrc/render.cu.
 """
 import ctypes
 import math
