@@ -201,6 +201,12 @@ int mfn_field_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const
 int mfn_field_bwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
                   const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale, float* d_xyz_params,
                   float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+/* tcnn.NetworkWithInputEncoding.forward for the fused shape (networks.py:36-57, called at :107): xyzs (n,3) f32 ->
+ * h_out (n,16) fp16, the raw (un-activated) outputs of grid encoding + 32->64->16 network, with x01 = (x - xyz_min) / (xyz_max -
+ * xyz_min) as in the other field calls (pass 0 / 1 for positions that are already in [0,1]).  Inference only: nothing is saved for a
+ * backward pass.  Returns an error for shapes mfn_field_is_fused() reports 0 for. */
+int mfn_geo_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
+                void* h_out, void* stream);
 /* density only (NGP.density, used by update_density_grid, networks.py:258) */
 int mfn_density_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
                     float* sigmas, void* workspace, int64_t workspace_bytes, void* stream);

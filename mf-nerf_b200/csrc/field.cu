@@ -259,6 +259,21 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     return grid_encode_backward(e, (const __half*)(ws + w.dfeats), m, cfg->grid.n_features, d_xyz_params + n_mlp1, overflow_flag, st);
 }
 
+extern "C" int mfn_geo_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
+                           void* h_out, void* stream) {
+    int rc = field_cfg_ok(cfg, "mfn_geo_fwd");
+    if (rc != MFN_OK) return rc;
+    if (n_max < 0) { set_error("mfn_geo_fwd: bad n_max"); return MFN_ERR_ARG; }
+    if (!use_fused(cfg)) { set_error("mfn_geo_fwd: only the fused shape (16 levels x 2 features, 64-wide one-hidden-layer network)"); return MFN_ERR_ARG; }
+    if (n_max == 0) return MFN_OK;
+    if (!xyz_params_h || !xyzs || !h_out) { set_error("mfn_geo_fwd: null pointer"); return MFN_ERR_ARG; }
+    GridMeta m;
+    if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_geo_fwd")) != MFN_OK) return rc;
+    FusedArgs f; make_fused(f, cfg, xyz_params_h, nullptr, xyzs, nullptr, n_max, n_dev);
+    f.h_out = (__half*)h_out;
+    return fused_field_forward(f, m, cfg->rgb_hidden, 3, (cudaStream_t)stream);
+}
+
 extern "C" int mfn_density_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
                                float* sigmas, void* workspace, int64_t workspace_bytes, void* stream) {
     int rc = field_cfg_ok(cfg, "mfn_density_fwd");

@@ -189,7 +189,8 @@ __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* t
 }
 
 // ------------------------------------------------------------------------------------------------------------------ forward
-// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma).
+// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma),
+// 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107).
 // 256 threads: thread t works on sample row t % 128 (= its TMEM lane); the two threads of a row split the 16 grid levels in the
 // gather phase and the 64 accumulator columns in the hidden-layer epilogues.  In training mode every published tile is also sent
 // to the blob with one bulk async store (shared -> global) issued by thread 0.
@@ -216,7 +217,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
     if ((int64_t)blockIdx.x >= n_tiles) return;      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
-    stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE != 2);
+    stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE < 2);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, nCols);
     fence_async_smem();
@@ -298,12 +299,14 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             o0.z = pack2(__uint_as_float(r[4]), __uint_as_float(r[5])); o0.w = pack2(__uint_as_float(r[6]), __uint_as_float(r[7]));
             o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9])); o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
             o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
-            if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
-            if (MODE != 2) {
+            if (MODE == 3) {
+                if (valid) { uint4* ho = reinterpret_cast<uint4*>(a.h_out + 16 * i); ho[0] = o0; ho[1] = o1; }
+            } else if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
+            if (MODE < 2) {
                 *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 16, 32)) = o0;
                 *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 24, 32)) = o1;
             }
-        } else if (MODE != 2) {
+        } else if (MODE < 2) {
             // the partner thread of the row meanwhile encodes the direction: SH of the normalised direction -> CAT[:, 0:16]
             // (networks.py:145-146); CAT may overlay H1, which the layer-2 MMA has finished reading
             mbar_wait(&bar, phase);
@@ -326,7 +329,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         tc_fence_before();
         __syncthreads();
         MFN_TS(7);
-        if (MODE == 2) continue;   // (uniform) density only
+        if (MODE >= 2) continue;   // (uniform) density only / raw outputs
         // ---- rgb layer 1: H2 = relu(CAT . W3^T)
         if (tid == 0) {
             tc_fence_after();
@@ -667,9 +670,10 @@ static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
     field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(a, m);
 }
 
-// mode: 0 inference, 1 training, 2 density only
+// mode: 0 inference, 1 training, 2 density only, 3 raw 16 outputs of the sigma network
 int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st) {
-    ProfScope ps(mode == 2 ? "density_fwd" : "field_fwd", st);
+    ProfScope ps(mode >= 2 ? "density_fwd" : "field_fwd", st);
+    if (mode == 3) { launch_fwd<1, 3>(a, m, st); return check_launch("mfn_geo_fwd(fused)", st); }
     if (rgb_hidden == 2) { if (mode == 0) launch_fwd<2, 0>(a, m, st); else if (mode == 1) launch_fwd<2, 1>(a, m, st); else launch_fwd<2, 2>(a, m, st); }
     else { if (mode == 0) launch_fwd<1, 0>(a, m, st); else if (mode == 1) launch_fwd<1, 1>(a, m, st); else launch_fwd<1, 2>(a, m, st); }
     return check_launch("mfn_field_fwd(fused)", st);

@@ -67,6 +67,7 @@ struct FusedArgs {
     const __half* w_rgb;     // [W3 64x32]([W4 64x64])[W5 16x64]
     float* sigmas; float* rgbs;
     float* rgbs_copy;        // training: second copy of rgbs kept in the workspace for the backward pass
+    __half* h_out;           // mode 3: (n, 16) fp16 raw outputs of the sigma network
     unsigned char* blobs;    // training: activation tiles, 64 KiB per 128 samples
     int rgb_act;
     // backward only

@@ -24,11 +24,7 @@ NEAR_DISTANCE = 0.01        # rendering.py:8
 G = 128                     # networks.py:27
 
 
-class FieldCfg(ctypes.Structure):
-    """mirror of `mfn_field_cfg` (include/mfnerf_b200.h)"""
-    _fields_ = [("grid", field_ops.GridCfg), ("sigma_width", ctypes.c_int32), ("sigma_hidden", ctypes.c_int32),
-                ("rgb_width", ctypes.c_int32), ("rgb_hidden", ctypes.c_int32), ("rgb_act", ctypes.c_int32),
-                ("xyz_min", ctypes.c_float * 3), ("xyz_max", ctypes.c_float * 3)]
+FieldCfg = field_ops.FieldCfg
 
 
 def make_field_cfg(scale, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, rgb_act="Sigmoid", grid="Hash",

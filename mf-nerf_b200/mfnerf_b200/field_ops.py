@@ -18,6 +18,13 @@ class GridCfg(ctypes.Structure):
                 ("n_tables", ctypes.c_int32)]
 
 
+class FieldCfg(ctypes.Structure):
+    """mirror of `mfn_field_cfg` (include/mfnerf_b200.h)"""
+    _fields_ = [("grid", GridCfg), ("sigma_width", ctypes.c_int32), ("sigma_hidden", ctypes.c_int32),
+                ("rgb_width", ctypes.c_int32), ("rgb_hidden", ctypes.c_int32), ("rgb_act", ctypes.c_int32),
+                ("xyz_min", ctypes.c_float * 3), ("xyz_max", ctypes.c_float * 3)]
+
+
 def make_grid_cfg(n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, grid_type="Hash", n_tables=1):
     if grid_type not in GRID_TYPES:
         raise NotImplementedError(f"grid type {grid_type!r} is not implemented (available: {sorted(GRID_TYPES)})")
@@ -83,3 +90,28 @@ def mlp_bwd(dout_h, x_h, acts, out_h, w_h, in_dim, width, n_hidden, act, dW_f32,
         call("mfn_mlp_bwd", ptr(dout_h), ptr(x_h), ptr(acts), ptr(out_h), ptr(w_h), in_dim, width, n_hidden, ACT[act], n, ptr(dx),
              ptr(dW_f32), stream_ptr(x_h.device))
     return dx
+
+
+def geo_cfg(grid_cfg, width, n_hidden):
+    """field config of a bare grid + network module whose inputs are already in [0,1] (tcnn.NetworkWithInputEncoding)"""
+    cfg = FieldCfg()
+    cfg.grid = grid_cfg
+    cfg.sigma_width, cfg.sigma_hidden = int(width), int(n_hidden)
+    cfg.rgb_width, cfg.rgb_hidden, cfg.rgb_act = 64, 1, 0
+    for k in range(3):
+        cfg.xyz_min[k] = 0.0; cfg.xyz_max[k] = 1.0
+    return cfg
+
+
+def geo_fused(cfg):
+    """True when mfn_geo_fwd runs this shape on the fused tcgen05 kernel"""
+    return int(_lib.lib.mfn_field_is_fused(ctypes.byref(cfg))) == 1
+
+
+def geo_fwd(x01, params_h, cfg):
+    """x01 (n,3) f32, params_h = fp16 [3072 network | table] -> (n,16) fp16 raw outputs, one fused kernel, nothing saved"""
+    n = x01.shape[0]
+    out = torch.empty(n, 16, dtype=torch.float16, device=x01.device)
+    with _dev_guard(x01):
+        call("mfn_geo_fwd", ctypes.byref(cfg), ptr(params_h), ptr(x01), n, None, ptr(out), stream_ptr(x01.device))
+    return out

@@ -234,6 +234,16 @@ class NetworkWithInputEncoding(nn.Module):
         p[self.n_mlp_params:].uniform_(-1e-4, 1e-4, generator=gen)
         self.params = nn.Parameter(p)
         self._cache = _ParamCache()
+        self._geo_cfg = F.geo_cfg(self.grid_cfg, self.width, self.n_hidden)
+        self._geo_fused = None
 
     def forward(self, x):
+        if not (torch.is_grad_enabled() and (self.params.requires_grad or x.requires_grad)):
+            # inference (NGP.density in update_density_grid, the whole test-time render): gather + both layers in ONE tcgen05
+            # kernel, no activations written.  Raw outputs only -- an output activation would need the unfused path.
+            if self._geo_fused is None:
+                self._geo_fused = F.geo_fused(self._geo_cfg) and self.out_act in ("None", "none", None)
+            if self._geo_fused and x.is_cuda:
+                out = F.geo_fwd(x.detach().float().contiguous(), self._cache.get(self.params), self._geo_cfg)
+                return out[:, :self.n_output_dims]
         return _EncMlpFn.apply(x, self.params, self)

@@ -57,3 +57,6 @@ def test_render_and_field_entry_points_validate_arguments():
     assert lib.mfn_render_iterations(ctypes.byref(cfg), None, None, None, None, 0, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None) == 0   # no rays: no-op
     assert lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1 << 20, 1) >= (1 << 20) * 512     # 64 KiB activation blob per 128 samples
     assert lib.mfn_field_fwd(ctypes.byref(cfg), None, None, None, None, 128, None, None, None, None, 0, None) == -2
+    assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 128, None, None, None) == -2 and b"null pointer" in lib.mfn_last_error()
+    assert lib.mfn_geo_fwd(ctypes.byref(wide), None, None, 128, None, None, None) == -2 and b"fused shape" in lib.mfn_last_error()
+    assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 0, None, None, None) == 0

@@ -128,6 +128,19 @@ def test_tcnn_dropin_modules_match_ngp_restatement():
         return sig, rgbs
     sig, rgbs = ours(x, d)
     assert rgbs.dtype == torch.float16 and rgbs.shape == (N, 3)
+    # inference (torch.no_grad, as in NGP.density under update_density_grid and the test-time render) takes the fused tcgen05 kernel
+    # (mfn_geo_fwd): same rounding points as the unfused kernels, another fp32 summation order -> agreement to a few fp16 ulps
+    from mfnerf_b200 import field_ops
+    assert field_ops.geo_fused(xyz_encoder._geo_cfg)
+    x01 = (x + scale) / (2 * scale)
+    h_train = xyz_encoder(x01)
+    with torch.no_grad():
+        h_inf = xyz_encoder(x01)
+        for n_ragged in (0, 1, 127, 129):                      # empty and ragged tiles
+            assert torch.equal(xyz_encoder(x01[:n_ragged]), h_inf[:n_ragged])
+    assert h_train.requires_grad and not h_inf.requires_grad and h_inf.dtype == torch.float16 and h_inf.shape == (N, 16)
+    torch.testing.assert_close(h_inf.float(), h_train.float(), rtol=1e-2, atol=5e-3)
+    assert float((h_inf.float() - h_train.detach().float()).abs().mean()) < 5e-4
     sig_r, rgbs_r = ref(x, d)
     torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=1e-3)
     torch.testing.assert_close(rgbs.float(), rgbs_r, rtol=2e-2, atol=3e-3)
