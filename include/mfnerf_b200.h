@@ -76,6 +76,32 @@ int mfn_grid_update(float* density_grid_cascade, const int32_t* cell_indices, co
                     void* stream);
 /* *mean_out = mean of the cells > 0 (l.268), device to device; scratch16 = 16 zero-initialised bytes the call leaves zeroed */
 int mfn_grid_mean_positive(const float* density_grid, int64_t n, float* scratch16, float* mean_out, void* stream);
+/* NGP.mark_invisible_cells (networks.py:199-240; called once before training, train.py:159-162): density_grid (cascades, G^3)
+ * f32 in morton order <- 0 where the cell centre is seen by at least one camera at depth >= near_distance inside the image and by
+ * none closer than that, else -1; count_grid (same shape, or NULL) <- fraction of the cameras covering the cell (self.count_grid).
+ * K (3,3) row-major intrinsics and poses (n_cams,3,4) camera-to-world are DEVICE arrays, as in the reference's call. */
+int mfn_grid_mark_invisible(const float* K, const float* poses, int32_t n_cams, int32_t img_w, int32_t img_h, int32_t cascades, float scale,
+                            int32_t grid_size, float near_distance, float* density_grid, float* count_grid, void* stream);
+
+/* ---- ray generation + batch sampling on the device ---------------------------------------------------
+ * One launch replaces the DataLoader item (datasets/base.py:22-34), the pose / direction gathers of NeRFSystem.forward
+ * (train.py:83-96) and get_ray_directions + get_rays (datasets/ray_utils.py:23-35, 60-68) for a data set resident in device memory:
+ *   ray i: image m = img_idxs[i], pixel p = pix_idxs[i]  (u = p % width, v = p / width)
+ *   direction = directions[p] if given, else ((u - cx + 0.5) / fx, (v - cy + 0.5) / fy, 1)
+ *   rays_d[i] = direction @ poses[m][:, :3]^T,  rays_o[i] = poses[m][:, 3],  rgb[i] = pixels[m][p][0:3]
+ * draw = 0: indices are read (img_idxs NULL -> every ray uses `image`; pix_idxs NULL -> ray i is pixel i: a whole test view);
+ * draw = 1: 'all_images' sampling, image and pixel drawn per ray; draw = 2: 'same_image', one image per call (base.py:24-29).
+ * Draws are counter-based on (seed, *call_counter, i); call_counter = uint64 in device memory or NULL, read only -- pass
+ * (char*)march_workspace + 16 to get a fresh batch on every step without host involvement.  img_idxs_out / pix_idxs_out (int64, or
+ * NULL) receive the indices used.  rgb / pixels may be NULL (no targets).  poses must be 16-byte aligned. */
+typedef struct mfn_camera {
+    float fx, fy, cx, cy;      /* K[0][0], K[1][1], K[0][2], K[1][2] */
+    int32_t width, height;
+} mfn_camera;
+int mfn_ray_batch(const mfn_camera* camera_host, const float* directions, const float* poses, int32_t n_images, const float* pixels,
+                  int32_t pixel_channels, const int64_t* img_idxs, const int64_t* pix_idxs, int32_t image, int32_t draw, uint64_t seed,
+                  const void* call_counter, int64_t n_rays, float* rays_o, float* rays_d, float* rgb, int64_t* img_idxs_out,
+                  int64_t* pix_idxs_out, void* stream);
 
 /* ---- intersection ---------------------------------------------------------------------------------- */
 /* replaces vren.ray_aabb_intersect (binding.cpp:4-16 -> intersection.cu:59-100).

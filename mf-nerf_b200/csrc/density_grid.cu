@@ -126,6 +126,66 @@ grid_mean_positive_kernel(const float* __restrict__ grid, int64_t n, float* __re
     }
 }
 
+// mark_invisible_cells (networks.py:199-240, run once before training, train.py:159-162): a cell is valid when at least one camera
+// sees its centre at depth >= near inside the image and no camera sees it closer than near; valid -> density 0, else -1 (cells at -1
+// are never updated nor marched).  One thread per cell (morton order, like get_all_cells l.157-170), cameras staged through shared
+// memory as world-to-camera rows [R^T | -R^T t] (l.215-216).
+constexpr int kCamChunk = 128;
+__global__ void __launch_bounds__(256)
+grid_mark_invisible_kernel(const float* __restrict__ K, const float* __restrict__ poses, int n_cams, float img_w, float img_h, float span, int grid_size,
+                           float near_d, int64_t n_cells, float* __restrict__ density, float* __restrict__ count_grid) {
+    __shared__ float cam[kCamChunk][12];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_cells;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+        const uint32_t mi = (uint32_t)i;
+        // xyzs = coords / (G-1) * 2 - 1 ;  xyzs_w = xyzs * (s - half_grid_size)      (l.221-224).  torch's CUDA division of a tensor by a
+        // python scalar multiplies by the fp32 reciprocal, and the reference runs this on the GPU: same here, to stay bit-compatible
+        const float inv = __fdiv_rn(1.f, (float)(grid_size - 1));
+        x = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)compact3(mi), inv), 2.f), 1.f), span);
+        y = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)compact3(mi >> 1), inv), 2.f), 1.f), span);
+        z = __fmul_rn(__fsub_rn(__fmul_rn(__fmul_rn((float)compact3(mi >> 2), inv), 2.f), 1.f), span);
+    }
+    float k[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) k[j] = __ldg(K + j);
+    int covered = 0;
+    bool too_near = false;
+    for (int c0 = 0; c0 < n_cams; c0 += kCamChunk) {
+        const int nc = min(kCamChunk, n_cams - c0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nc; t += blockDim.x) {
+            const float* P = poses + 12 * (size_t)(c0 + t);          // c2w rows [R_a0 R_a1 R_a2 t_a]
+            float R[3][3], T[3];
+            for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) R[a][b] = P[4 * a + b]; T[a] = P[4 * a + 3]; }
+            for (int a = 0; a < 3; ++a) {                            // w2c_R = R^T ; w2c_T = -(R^T t)
+                cam[t][4 * a] = R[0][a]; cam[t][4 * a + 1] = R[1][a]; cam[t][4 * a + 2] = R[2][a];
+                cam[t][4 * a + 3] = -fmaf(R[2][a], T[2], fmaf(R[1][a], T[1], R[0][a] * T[0]));
+            }
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int t = 0; t < nc; ++t) {
+            const float* w = cam[t];
+            const float xc = fmaf(w[2], z, fmaf(w[1], y, w[0] * x)) + w[3];        // xyzs_c = w2c_R @ xyzs_w + w2c_T   (l.225)
+            const float yc = fmaf(w[6], z, fmaf(w[5], y, w[4] * x)) + w[7];
+            const float zc = fmaf(w[10], z, fmaf(w[9], y, w[8] * x)) + w[11];
+            const float ud = fmaf(k[2], zc, fmaf(k[1], yc, k[0] * xc));            // uvd = K @ xyzs_c                  (l.226)
+            const float vd = fmaf(k[5], zc, fmaf(k[4], yc, k[3] * xc));
+            const float d = fmaf(k[8], zc, fmaf(k[7], yc, k[6] * xc));
+            const float u = __fdiv_rn(ud, d), v = __fdiv_rn(vd, d);                // uv = uvd[:2] / uvd[2]             (l.227)
+            const bool in_image = (d >= 0.f) && (u >= 0.f) && (u < img_w) && (v >= 0.f) && (v < img_h);
+            covered += (in_image && d >= near_d) ? 1 : 0;                          // l.231
+            too_near |= in_image && (d < near_d);                                  // l.236-238
+        }
+    }
+    if (!live) return;
+    const float count = __fmul_rn((float)covered, __fdiv_rn(1.f, (float)n_cams)); // l.233-234 (sum / N_cams, scalar divisor: reciprocal multiply as above)
+    if (count_grid) count_grid[i] = count;
+    density[i] = (count > 0.f && !too_near) ? 0.f : -1.f;                          // l.240-242
+}
+
 static inline int dg_grid(int64_t n) {
     int64_t b = ceil_div(n, 256);
     const int64_t cap = (int64_t)kNumSMs * 8;
@@ -176,4 +236,20 @@ extern "C" int mfn_grid_mean_positive(const float* density_grid, int64_t n, floa
     if (!density_grid || !scratch16 || !mean_out) { set_error("mfn_grid_mean_positive: null pointer"); return MFN_ERR_ARG; }
     grid_mean_positive_kernel<<<dg_grid(n > 0 ? n : 1), 256, 0, (cudaStream_t)stream>>>(density_grid, n, scratch16, reinterpret_cast<unsigned int*>(scratch16 + 2), mean_out);
     return check_launch("mfn_grid_mean_positive", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_grid_mark_invisible(const float* K, const float* poses, int32_t n_cams, int32_t img_w, int32_t img_h, int32_t cascades, float scale,
+                                       int32_t grid_size, float near_distance, float* density_grid, float* count_grid, void* stream) {
+    if (n_cams < 1 || img_w < 1 || img_h < 1 || cascades < 1 || grid_size < 2 || grid_size > 1024) { set_error("mfn_grid_mark_invisible: bad argument"); return MFN_ERR_ARG; }
+    if (!K || !poses || !density_grid) { set_error("mfn_grid_mark_invisible: null pointer"); return MFN_ERR_ARG; }
+    const int64_t n_cells = (int64_t)grid_size * grid_size * grid_size;
+    for (int c = 0; c < cascades; ++c) {
+        const double s = fmin(exp2((double)(c - 1)), (double)scale);       // python floats: s = min(2**(c-1), scale); half = s / G  (l.222-223)
+        const float span = (float)(s - s / (double)grid_size);
+        grid_mark_invisible_kernel<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+            K, poses, n_cams, (float)img_w, (float)img_h, span, grid_size, near_distance, n_cells, density_grid + (size_t)c * n_cells,
+            count_grid ? count_grid + (size_t)c * n_cells : nullptr);
+        if (c) note_launch(1);
+    }
+    return check_launch("mfn_grid_mark_invisible", (cudaStream_t)stream);
 }

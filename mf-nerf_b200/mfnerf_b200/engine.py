@@ -370,6 +370,39 @@ class NGPEngine:
         self._run_forward_backward()
         self._optimizer_step(lr)
 
+    # ------------------------------------------------------------------------------------------------ resident data set
+    def attach_dataset(self, dataset, seed=0):
+        """`dataset`: mfnerf_b200.dataset.ResidentDataset.  train_step_resident() then draws its own batches on the device."""
+        self.dataset, self._batch_seed = dataset, int(seed)
+
+    def _draw_batch(self):
+        """one launch: random (image, pixel) per ray -> rays_o, rays_d, target straight into the step's static buffers
+        (datasets/base.py:22-34 + train.py:83-96 + ray_utils.py:23-35, 60-68); the marcher's call counter makes every step's draw new"""
+        from . import dataset as mds
+        ds = self.dataset
+        mds.ray_batch(ds.camera, ds.poses, self.n_rays, pixels=ds.pixels, strategy=ds.strategy, seed=self._batch_seed,
+                      call_counter=self.march_ws[16:], rays_o=self.rays_o, rays_d=self.rays_d, rgb=self.target)
+
+    def train_step_resident(self, lr=None, global_step=None):
+        """as train_step, with the batch drawn on the device from the attached data set: the step has no host-to-device traffic"""
+        if global_step is None:
+            global_step = self.step_count
+        if self.dp:
+            return self._step_dp(self._draw_batch, lr, global_step)
+        if global_step % 16 == 0:
+            self.update_density_grid(warmup=global_step < 256)
+        self._draw_batch()
+        self._run_forward_backward()
+        self._optimizer_step(lr)
+
+    def mark_invisible_cells(self, K, poses, img_wh):
+        """networks.py:199-240 (train.py:159-162, once before training): density_grid <- 0 / -1, self.count_grid <- camera coverage"""
+        K = torch.as_tensor(K, dtype=torch.float32).to(self.dev).contiguous()
+        poses = torch.as_tensor(poses, dtype=torch.float32).to(self.dev).contiguous()
+        self.count_grid = torch.zeros_like(self.density_grid)
+        call("mfn_grid_mark_invisible", ptr(K), ptr(poses), poses.shape[0], int(img_wh[0]), int(img_wh[1]), self.cascades, self.scale, G, NEAR_DISTANCE,
+             ptr(self.density_grid), ptr(self.count_grid), stream_ptr(self.dev))
+
     # ------------------------------------------------------------------------------------------------ data-parallel step
     def _dp_setup(self):
         """ZeRO-1 style sharding of the optimiser over the ranks: reduce-scatter of the flat fp32 gradient, Adam on this rank's

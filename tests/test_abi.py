@@ -60,3 +60,12 @@ def test_render_and_field_entry_points_validate_arguments():
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 128, None, None, None) == -2 and b"null pointer" in lib.mfn_last_error()
     assert lib.mfn_geo_fwd(ctypes.byref(wide), None, None, 128, None, None, None) == -2 and b"fused shape" in lib.mfn_last_error()
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 0, None, None, None) == 0
+    # ray generation / mark_invisible_cells
+    from mfnerf_b200.dataset import Camera
+    cam = Camera(100.0, 100.0, 32.0, 24.0, 64, 48)
+    rb = lambda cam, n_img, n, draw=0, image=0: lib.mfn_ray_batch(ctypes.byref(cam), None, None, n_img, None, 0, None, None, image, draw, 1, None, n, None, None, None, None, None, None)
+    assert rb(cam, 4, 0) == 0                                               # no rays: no-op
+    assert rb(cam, 4, 16) == -2 and b"null pointer" in lib.mfn_last_error()
+    assert rb(cam, 0, 16) == -2 and rb(cam, 4, 16, draw=3) == -2 and rb(Camera(0.0, 1.0, 0.0, 0.0, 8, 8), 4, 16) == -2
+    assert lib.mfn_grid_mark_invisible(None, None, 4, 64, 48, 1, 0.5, 128, 0.01, None, None, None) == -2
+    assert lib.mfn_grid_mark_invisible(None, None, 0, 64, 48, 1, 0.5, 128, 0.01, None, None, None) == -2 and b"bad argument" in lib.mfn_last_error()

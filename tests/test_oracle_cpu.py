@@ -151,3 +151,25 @@ def test_oracle_pinned_to_reference_kernels(path):
     mine = vc.run_oracle(sc)
     problems = vc.compare(mine, g, exact_expf=False, label=os.path.basename(path) + ": ")
     assert not problems, "\n".join(problems)
+
+
+def test_dataset_oracle_pinned_to_reference_python():
+    """oracle/dataset_ref.py against tests/golden/dataset_ref.npz = outputs of the reference's own get_ray_directions / get_rays /
+    NGP.mark_invisible_cells (tests/golden/make_golden_dataset.py)"""
+    from oracle import dataset_ref as dr
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_ref.npz"))
+    W, H = (int(v) for v in g["img_wh"])
+    assert np.array_equal(dr.ray_directions(H, W, g["K"]), g["directions"])                       # pixel-centre directions: bit-exact
+    o, d, _ = dr.rays_from_indices(g["K"], (W, H), g["poses"], g["img_idxs"], g["pix_idxs"])
+    assert np.array_equal(o, g["rays_o"])
+    # the rotation is a 3-term fp32 dot product; torch's CPU bmm and an FMA chain round differently in the last bit (tolerance: 2 ulp of 1)
+    np.testing.assert_allclose(d, g["rays_d"], rtol=0, atol=2.4e-7)
+    vo, vd, _ = dr.rays_from_indices(g["K"], (W, H), g["poses"], np.full(W * H, 5), np.arange(W * H))
+    assert np.array_equal(vo, g["view_o"])
+    np.testing.assert_allclose(vd, g["view_d"], rtol=0, atol=2.4e-7)
+    dens, cnt, fragile = dr.mark_invisible_cells(g["K"], g["mi_poses"], (W, H), int(g["mi_cascades"]), float(g["mi_scale"]), int(g["mi_G"]),
+                                                 float(g["mi_near"]))
+    assert set(np.unique(dens)) <= {0.0, -1.0} and 0 < (dens == 0).mean() < 1
+    assert fragile.mean() < 0.02
+    assert np.array_equal(dens[~fragile], g["mi_density"][~fragile]) and np.array_equal(cnt[~fragile], g["mi_count"][~fragile])
+    assert (dens != g["mi_density"]).sum() <= 2                                                   # here they agree everywhere; fragile cells may flip
