@@ -172,6 +172,11 @@ int mfn_distortion_loss_bw(const float* dL_dloss, const float* ws_inclusive_scan
 
 /* ---- field: encodings (replace tcnn's HashGrid / SphericalHarmonics encodings, networks.py:36-47,60-67) ------- */
 #define MFN_GRID_HASH 0
+/* MixedFeature grid of the MF-NeRF fork (networks.py:40-46 `--grid MixedFeature --N_tables K`).  The fork's tiny-cuda-nn is not part
+ * of the reference tree, so the semantics are DEFINED here (parity unpinned): level l lives in table k = l*K/L; the K tables have 2^T
+ * entries each and are always hashed; a vertex is hashed by its coordinates in the table's canonical grid (the finest level of the
+ * table): canonical vertex = round((v - 0.5) * scale_canonical / scale_l + 0.5).  Runs on the unfused field kernels. */
+#define MFN_GRID_MIXED 1
 typedef struct mfn_grid_cfg {
     int32_t n_levels;            /* L */
     int32_t n_features;          /* F: 1, 2, 4 or 8 */
@@ -179,7 +184,7 @@ typedef struct mfn_grid_cfg {
     int32_t base_resolution;     /* N_min */
     double per_level_scale;      /* b */
     int32_t grid_type;           /* MFN_GRID_* */
-    int32_t n_tables;            /* the MF-NeRF fork's knob; 1 for the plain hash grid */
+    int32_t n_tables;            /* K of the MixedFeature grid (1 <= K <= L); ignored by the plain hash grid */
 } mfn_grid_cfg;
 /* HOST helper: level table.  offsets_host[L+1] (entries), resolutions_host[L], scales_host[L] may be NULL.
  * Returns the total number of table entries (parameters = entries * F), <0 on error. */

@@ -26,7 +26,10 @@ int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
     if (cfg->n_features != 1 && cfg->n_features != 2 && cfg->n_features != 4 && cfg->n_features != 8) {
         set_error("%s: n_features_per_level must be 1, 2, 4 or 8", who); return MFN_ERR_ARG;
     }
-    if (cfg->grid_type != MFN_GRID_HASH) { set_error("%s: unsupported grid_type %d", who, cfg->grid_type); return MFN_ERR_ARG; }
+    if (cfg->grid_type != MFN_GRID_HASH && cfg->grid_type != MFN_GRID_MIXED) { set_error("%s: unsupported grid_type %d", who, cfg->grid_type); return MFN_ERR_ARG; }
+    if (cfg->grid_type == MFN_GRID_MIXED && (cfg->n_tables < 1 || cfg->n_tables > cfg->n_levels)) {
+        set_error("%s: MixedFeature grid needs 1 <= n_tables <= n_levels (got %d)", who, cfg->n_tables); return MFN_ERR_ARG;
+    }
     // tcnn keeps per_level_scale as a float; the level scale is evaluated in double from that float and rounded to
     // float once, which makes res_l robust against last-bit noise when scale_l is (nearly) an integer.
     const double log2b = log2((double)(float)cfg->per_level_scale);
@@ -42,11 +45,29 @@ int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who) {
         const uint64_t T = 1ull << cfg->log2_hashmap_size;
         if (entries > T) entries = T;
         if (cells > entries) m->hashed |= 1u << l;
-        m->offset[l] = (uint32_t)off; m->res[l] = res; m->scale[l] = s;
+        m->offset[l] = (uint32_t)off; m->res[l] = res; m->scale[l] = s; m->size[l] = (uint32_t)entries; m->canon[l] = 0.f;
         off += entries;
         if (off > 0xffffffffull) { set_error("%s: grid too large", who); return MFN_ERR_ARG; }
     }
     m->offset[cfg->n_levels] = (uint32_t)off;
+    m->mixed = 0;
+    if (cfg->grid_type == MFN_GRID_MIXED) {
+        // MixedFeature (the MF-NeRF fork's grid; semantics defined HERE): level l lives in table k = l * n_tables / L,
+        // every table has 2^T entries and is always hashed; vertices are hashed by their coordinates in the table's canonical grid
+        // (its finest level), so coincident vertices of the levels of one table share a feature
+        const uint64_t T = 1ull << cfg->log2_hashmap_size;
+        if (T * (uint64_t)cfg->n_tables > 0xffffffffull) { set_error("%s: grid too large", who); return MFN_ERR_ARG; }
+        m->mixed = 1;
+        m->hashed = cfg->n_levels >= 32 ? 0xffffffffu : ((1u << cfg->n_levels) - 1u);
+        for (int l = 0; l < cfg->n_levels; ++l) {
+            const int k = l * cfg->n_tables / cfg->n_levels;
+            int lc = l;
+            while (lc + 1 < cfg->n_levels && (lc + 1) * cfg->n_tables / cfg->n_levels == k) ++lc;
+            m->offset[l] = (uint32_t)((uint64_t)k * T); m->size[l] = (uint32_t)T;
+            m->canon[l] = m->scale[lc] / m->scale[l];
+        }
+        m->offset[cfg->n_levels] = (uint32_t)(T * (uint64_t)cfg->n_tables);
+    }
     return MFN_OK;
 }
 
@@ -109,7 +130,7 @@ grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restri
     const int l = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const uint32_t res = m.res[l], size = m.size[l];
     const bool hashed = (m.hashed >> l) & 1u;
     float* lvl = dgrid + (size_t)m.offset[l] * F;
     const int64_t n_pad = (n + 31) / 32 * 32;   // whole warps stay in the loop (shuffles below)
@@ -157,9 +178,15 @@ grid_encode_bwd_kernel(const __grid_constant__ EncArgs e, const __half* __restri
                 for (int f = 0; f < F; ++f) { const float o = __shfl_down_sync(0xffffffffu, v[c][f], d); if (take) v[c][f] += o; }
         }
         if (head) {
+            uint32_t cx[2] = {gx, gx + 1u}, cy[2] = {gy, gy + 1u}, cz[2] = {gz, gz + 1u};
+            if (m.mixed) {
+                const float r = m.canon[l];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { cx[k] = canon_vertex(cx[k], r); cy[k] = canon_vertex(cy[k], r); cz[k] = canon_vertex(cz[k], r); }
+            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                const uint32_t idx = grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed);
+                const uint32_t idx = grid_index(cx[c & 1], cy[(c >> 1) & 1], cz[c >> 2], res, size, hashed);
                 atomic_add_vec<F>(lvl + (size_t)idx * F, v[c]);
             }
         }
@@ -208,7 +235,7 @@ grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_
     const int l = blockIdx.y;
     const int lane = threadIdx.x & 31, xb = lane & 1;
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const uint32_t res = m.res[l], size = m.size[l];
     const bool hashed = (m.hashed >> l) & 1u;
     const uint32_t mask = size - 1u, r2 = res * res;
     float2* lvl = reinterpret_cast<float2*>(dgrid) + m.offset[l];

@@ -650,7 +650,7 @@ static int num_sms() {
 }
 
 bool fused_field_supported(const mfn_field_cfg* c) {
-    return c->grid.n_levels == 16 && c->grid.n_features == 2 && c->sigma_width == 64 && c->sigma_hidden == 1 && c->rgb_width == 64 &&
+    return c->grid.grid_type == MFN_GRID_HASH && c->grid.n_levels == 16 && c->grid.n_features == 2 && c->sigma_width == 64 && c->sigma_hidden == 1 && c->rgb_width == 64 &&
            (c->rgb_hidden == 1 || c->rgb_hidden == 2);
 }
 int fused_bwd_max_ctas() { return 2 * num_sms(); }

@@ -13,6 +13,11 @@ struct GridMeta {
     float scale[kMaxLevels];
     uint32_t hashed;                  // bit l set: level l is hashed
     int n_levels;
+    // MixedFeature grid (MFN_GRID_MIXED): several levels share one hash table; size[l] = entries of level l's table
+    // (= offset[l+1] - offset[l] for the plain hash grid), canon[l] = scale of the table's canonical (finest) level / scale[l]
+    uint32_t size[kMaxLevels];
+    float canon[kMaxLevels];
+    int mixed;
 };
 int build_grid_meta(const mfn_grid_cfg* cfg, GridMeta* m, const char* who);
 

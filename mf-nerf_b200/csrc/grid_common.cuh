@@ -12,6 +12,13 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
     return idx % size;
 }
 
+// MixedFeature index transformation: vertex v of a level sits at x = (v - 0.5) / scale_l; its canonical-grid vertex is the one
+// nearest to that point, round((v - 0.5) * scale_c / scale_l + 0.5).  Separately rounded multiply and add (no FMA) so that the torch
+// restatement reproduces the integer result bit for bit.  For the canonical level itself (ratio 1) this is the identity.
+__device__ __forceinline__ uint32_t canon_vertex(uint32_t v, float ratio) {
+    return (uint32_t)(int)floorf(__fadd_rn(__fmul_rn(__fsub_rn((float)v, 0.5f), ratio), 1.0f));
+}
+
 template <int F> struct FeatVec;
 template <> struct FeatVec<1> { using T = unsigned short; };
 template <> struct FeatVec<2> { using T = uint32_t; };
@@ -29,17 +36,23 @@ __device__ __forceinline__ void add_weighted(float (&acc)[F], const typename Fea
 template <int F>
 __device__ __forceinline__ void encode_level(const __half* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, float (&acc)[F]) {
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], size = m.offset[l + 1] - m.offset[l];
+    const uint32_t res = m.res[l], size = m.size[l];
     const bool hashed = (m.hashed >> l) & 1u;
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = px - fx, wy = py - fy, wz = pz - fz;
     const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    uint32_t cx[2] = {gx, gx + 1u}, cy[2] = {gy, gy + 1u}, cz[2] = {gz, gz + 1u};
+    if (m.mixed) {
+        const float r = m.canon[l];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { cx[k] = canon_vertex(cx[k], r); cy[k] = canon_vertex(cy[k], r); cz[k] = canon_vertex(cz[k], r); }
+    }
     const typename FeatVec<F>::T* lvl = reinterpret_cast<const typename FeatVec<F>::T*>(table) + m.offset[l];
     typename FeatVec<F>::T v[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-        v[c] = __ldg(lvl + grid_index(gx + (c & 1), gy + ((c >> 1) & 1), gz + (c >> 2), res, size, hashed));
+        v[c] = __ldg(lvl + grid_index(cx[c & 1], cy[(c >> 1) & 1], cz[c >> 2], res, size, hashed));
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
 #pragma unroll

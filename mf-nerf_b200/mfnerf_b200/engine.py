@@ -46,13 +46,14 @@ def _pad(n, m=8):
 class NGPEngine:
     def __init__(self, scale=0.5, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, n_rays=8192,
                  device="cuda", lr=1e-2, loss_scale=1024.0, distortion_w=0.0, lambda_opacity=1e-3, sample_capacity=None, seed=1337,
-                 exp_step_factor=None, T_threshold=1e-4, world_size=1, process_group=None, force_dp_path=False, pipelined=True):
+                 exp_step_factor=None, T_threshold=1e-4, world_size=1, process_group=None, force_dp_path=False, pipelined=True,
+                 grid="Hash", n_tables=1):
         self.dev = torch.device(device)
         self.scale, self.n_rays = float(scale), int(n_rays)
         self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)                     # networks.py:26
         self.esf = (1.0 / 256 if scale > 0.5 else 0.0) if exp_step_factor is None else float(exp_step_factor)   # train.py:100-101
         self.bg = (ctypes.c_float * 3)(*([1.0, 1.0, 1.0] if self.esf == 0 else [0.0, 0.0, 0.0]))           # rendering.py:153-161
-        self.cfg = make_field_cfg(scale, L, F, log2_T, N_min, N_max, rgb_channels, rgb_layers)
+        self.cfg = make_field_cfg(scale, L, F, log2_T, N_min, N_max, rgb_channels, rgb_layers, grid=grid, n_tables=n_tables)     # opt.py:71-85 --grid / --N_tables
         self.lr, self.loss_scale, self.T_thr = lr, float(loss_scale), float(T_threshold)
         self.distortion_w, self.lambda_opacity = float(distortion_w), float(lambda_opacity)
         self.world_size, self.pg = world_size, process_group
@@ -584,6 +585,8 @@ class NGPEngine:
         wavefront of csrc/render.cu.  The host only looks at the alive count between batches of `iterations_per_batch` iterations."""
         d = self.dev
         self._wait_comm()
+        if _lib.lib.mfn_field_is_fused(ctypes.byref(self.cfg)) != 1:      # shapes outside the fused kernels (MixedFeature grid, 128-wide rgb net):
+            return self.render_reference_loop(rays_o, rays_d, max_samples, T_threshold)      # the same loop, one kernel launch per operation
         N = rays_o.shape[0]
         rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
         min_samples = (1 if self.esf == 0 else 4) if min_chunk is None else int(min_chunk)     # rendering.py:70

@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import call, ptr, stream_ptr
 
 ACT = {"None": 0, "none": 0, None: 0, "Sigmoid": 1, "sigmoid": 1, "Exponential": 2, "exp": 2}
-GRID_TYPES = {"Hash": 0}
+GRID_TYPES = {"Hash": 0, "MixedFeature": 1}      # MFN_GRID_HASH, MFN_GRID_MIXED ("Window": semantics unknown, not implemented)
 
 
 class GridCfg(ctypes.Structure):

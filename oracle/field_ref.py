@@ -17,9 +17,11 @@ import torch
 PRIMES = (1, 2654435761, 805459861)
 
 
-def grid_layout(n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale):
+def grid_layout(n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, grid_type="Hash", n_tables=1):
     """per-level (offset, entries, resolution, scale).  tcnn: scale = exp2(l*log2(b))*N_min - 1 (b held as float),
-    res = ceil(scale)+1, entries = min(round_up(res^3, 8), 2^T)."""
+    res = ceil(scale)+1, entries = min(round_up(res^3, 8), 2^T).
+    grid_type "MixedFeature" (spec defined in include/mfnerf_b200.h, parity unpinned): level l lives in table k = l*K/L of 2^T
+    entries, always hashed, vertices hashed by their coordinates in the table's canonical (finest) level."""
     log2b = math.log2(float(np.float32(per_level_scale)))
     off, levels = 0, []
     for l in range(n_levels):
@@ -29,11 +31,29 @@ def grid_layout(n_levels, n_features, log2_hashmap_size, base_resolution, per_le
         entries = min((min(cells, 0x7fffffff) + 7) // 8 * 8, 1 << log2_hashmap_size)
         levels.append(dict(offset=off, entries=entries, res=res, scale=scale, hashed=cells > entries))
         off += entries
+    if grid_type == "MixedFeature":
+        T = 1 << log2_hashmap_size
+        for l, lv in enumerate(levels):
+            k = l * n_tables // n_levels
+            lc = max(j for j in range(n_levels) if j * n_tables // n_levels == k)
+            lv.update(offset=k * T, entries=T, hashed=True, canon=float(np.float32(levels[lc]["scale"]) / np.float32(lv["scale"])))
+        off = n_tables * T
+    elif grid_type != "Hash":
+        raise NotImplementedError(grid_type)
     return levels, off
+
+
+def _canon(v, ratio):
+    """MixedFeature index transformation: level vertex -> nearest vertex of the table's canonical grid, in fp32 like the kernel:
+    floor(fl(fl(v - 0.5) * ratio) + 1)"""
+    r = torch.tensor(ratio, dtype=torch.float32, device=v.device)
+    return torch.floor((v.to(torch.float32) - 0.5) * r + 1.0).to(torch.int64)
 
 
 def _corner_indices(gx, gy, gz, lv):
     """(N,) int64 coords -> (N,) int64 table index within the level (tcnn grid_index)"""
+    if "canon" in lv:
+        gx, gy, gz = _canon(gx, lv["canon"]), _canon(gy, lv["canon"]), _canon(gz, lv["canon"])
     if lv["hashed"]:
         m = 0xFFFFFFFF
         idx = ((gx * PRIMES[0]) & m) ^ ((gy * PRIMES[1]) & m) ^ ((gz * PRIMES[2]) & m)
@@ -110,12 +130,12 @@ class NGPRef(torch.nn.Module):
     """torch restatement of models/networks.py:12-155 (NGP.density / NGP.forward) on top of the functions above.
     Parameters are fp32 masters; forward uses their fp16-rounded values like tcnn does."""
 
-    def __init__(self, scale, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, params=None):
+    def __init__(self, scale, L=16, F=2, log2_T=19, N_min=16, N_max=2048, rgb_channels=64, rgb_layers=2, params=None, grid="Hash", n_tables=1):
         super().__init__()
         self.scale = scale
         self.L, self.F = L, F
         self.b = float(np.exp(np.log(N_max * scale / N_min) / (L - 1)))
-        self.levels, self.entries = grid_layout(L, F, log2_T, N_min, self.b)
+        self.levels, self.entries = grid_layout(L, F, log2_T, N_min, self.b, grid, n_tables)
         self.rgb_channels, self.rgb_layers = rgb_channels, rgb_layers
         n_xyz = 64 * (L * F) + 16 * 64 + self.entries * F
         n_rgb = rgb_channels * 32 + (rgb_layers - 1) * rgb_channels ** 2 + 16 * rgb_channels

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -60,6 +62,13 @@ def test_render_and_field_entry_points_validate_arguments():
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 128, None, None, None) == -2 and b"null pointer" in lib.mfn_last_error()
     assert lib.mfn_geo_fwd(ctypes.byref(wide), None, None, 128, None, None, None) == -2 and b"fused shape" in lib.mfn_last_error()
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 0, None, None, None) == 0
+    # MixedFeature grid: K tables of 2^T entries; runs on the unfused kernels
+    from mfnerf_b200 import field_ops
+    mixed = make_field_cfg(0.5, log2_T=17, grid="MixedFeature", n_tables=8)
+    assert field_ops.grid_layout(mixed.grid)[0] == 8 << 17 and lib.mfn_field_is_fused(ctypes.byref(mixed)) == 0
+    assert lib.mfn_grid_layout(ctypes.byref(field_ops.make_grid_cfg(16, 2, 17, 16, 1.3, "MixedFeature", 0)), None, None, None) == -1
+    with pytest.raises(NotImplementedError):
+        field_ops.make_grid_cfg(16, 2, 17, 16, 1.3, "Window", 1)
     # ray generation / mark_invisible_cells
     from mfnerf_b200.dataset import Camera
     cam = Camera(100.0, 100.0, 32.0, 24.0, 64, 48)

@@ -14,19 +14,24 @@ from oracle import field_ref as fr
 pytestmark = pytest.mark.gpu
 
 
-def _grid_case(scale, T, F=2, L=16):
+def _grid_case(scale, T, F=2, L=16, grid="Hash", n_tables=1):
     from mfnerf_b200 import field_ops as ops
     b = float(np.exp(np.log(2048 * scale / 16) / (L - 1)))
-    cfg = ops.make_grid_cfg(L, F, T, 16, b)
-    levels, entries = fr.grid_layout(L, F, T, 16, b)
-    assert ops.grid_layout(cfg)[0] == entries
+    cfg = ops.make_grid_cfg(L, F, T, 16, b, grid, n_tables)
+    levels, entries = fr.grid_layout(L, F, T, 16, b, grid, n_tables)
+    total, off, res, _ = ops.grid_layout(cfg)
+    assert total == entries and off[:L] == [lv["offset"] for lv in levels] and res == [lv["res"] for lv in levels]
     return cfg, levels, entries
 
 
-@pytest.mark.parametrize("scale,T,F,L", [(0.5, 19, 2, 16), (16.0, 21, 2, 16), (0.5, 15, 4, 8), (0.5, 14, 1, 16), (4.0, 16, 8, 4)])
-def test_grid_encode_forward_backward(scale, T, F, L):
+# the last four: the MF-NeRF fork's MixedFeature grid (spec defined in include/mfnerf_b200.h; the scripts use L16 F2 T20-22, 8 tables)
+@pytest.mark.parametrize("scale,T,F,L,grid,n_tables", [(0.5, 19, 2, 16, "Hash", 1), (16.0, 21, 2, 16, "Hash", 1), (0.5, 15, 4, 8, "Hash", 1),
+                                                        (0.5, 14, 1, 16, "Hash", 1), (4.0, 16, 8, 4, "Hash", 1),
+                                                        (0.5, 20, 2, 16, "MixedFeature", 8), (16.0, 18, 2, 16, "MixedFeature", 4),
+                                                        (0.5, 16, 4, 8, "MixedFeature", 8), (0.5, 17, 2, 16, "MixedFeature", 1)])
+def test_grid_encode_forward_backward(scale, T, F, L, grid, n_tables):
     from mfnerf_b200 import field_ops as ops
-    cfg, levels, entries = _grid_case(scale, T, F, L)
+    cfg, levels, entries = _grid_case(scale, T, F, L, grid, n_tables)
     g = torch.Generator().manual_seed(0)
     N = 4099
     x = torch.rand(N, 3, generator=g)
@@ -154,3 +159,40 @@ def test_tcnn_dropin_modules_match_ngp_restatement():
         assert big.sum() > 50
         assert (err[big] <= 8e-2 * want.abs()[big] + 2e-3 * sc).all(), (name, err[big].max().item(), sc)
         assert err.max().item() <= 3e-2 * sc, (name, err.max().item(), sc)
+
+
+def test_tcnn_dropin_mixed_feature_grid():
+    """`--grid MixedFeature --N_tables 8` as the reference's scripts configure it (networks.py:36-57): K * 2^T * F grid parameters, forward
+    and parameter gradients against the restatement of the same spec"""
+    import tinycudann as tcnn
+    scale, T, K = 0.5, 16, 8
+    b = float(np.exp(np.log(2048 * scale / 16) / 15))
+    enc = tcnn.NetworkWithInputEncoding(3, 16, {"otype": "MixedFeatureGrid", "type": "MixedFeature", "n_levels": 16, "n_features_per_level": 2,
+                                                "log2_hashmap_size": T, "base_resolution": 16, "n_tables": K, "per_level_scale": b,
+                                                "interpolation": "Linear"},
+                                        {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64,
+                                         "n_hidden_layers": 1}).cuda()
+    assert enc.params.shape[0] - 3072 == K * (1 << T) * 2
+    with torch.no_grad():
+        enc.params[3072:].uniform_(-0.5, 0.5)
+    levels, entries = fr.grid_layout(16, 2, T, 16, b, "MixedFeature", K)
+    x = torch.rand(3000, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    h = enc(x)
+    with torch.no_grad():
+        h_inf = enc(x)                                      # no fused kernel for this grid: inference takes the same kernels
+    assert torch.equal(h_inf, h.detach())
+    p = enc.params.detach().clone().requires_grad_(True)
+    ph = fr._h(p)
+    want = fr._h(fr.mlp(fr._h(fr.grid_encode(x, ph[3072:], levels, 2)), ph[:3072], 32, 64, 1))
+    torch.testing.assert_close(h.float(), want, rtol=3e-2, atol=2e-3)
+    gout = torch.randn(3000, 16, generator=torch.Generator().manual_seed(3)).cuda() * 1e-2
+    (h.float() * gout).sum().backward()
+    (want * gout).sum().backward()
+    got, ref = enc.params.grad, p.grad
+    sc = ref.abs().max().item()
+    big = ref.abs() > 5e-2 * sc
+    assert big.sum() > 50 and (got - ref).abs().max().item() <= 3e-2 * sc
+    assert ((got - ref).abs()[big] <= 8e-2 * ref.abs()[big] + 2e-3 * sc).all()
+    with pytest.raises(NotImplementedError):
+        tcnn.Encoding(3, {"otype": "WindowGrid", "type": "Window", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15,
+                          "base_resolution": 16, "n_tables": 1, "per_level_scale": b})
