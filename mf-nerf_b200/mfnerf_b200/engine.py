@@ -158,6 +158,28 @@ class NGPEngine:
         if "density_grid" in sd:
             self.density_grid.copy_(sd["density_grid"])
 
+    def save_checkpoint(self, path, slim=True, model_name="model"):
+        """writes what the reference's trainer leaves behind (a Lightning checkpoint: {'state_dict': {'model.<key>': tensor}}); slim=True
+        drops `density_grid` like utils.slim_ckpt (utils.py:30-41).  utils.load_ckpt(model, path) of the reference reads it back."""
+        sd = {f"{model_name}.{k}": v.cpu() for k, v in self.state_dict().items() if not (slim and k == "density_grid")}
+        torch.save({"state_dict": sd}, path)
+
+    def load_checkpoint(self, ckpt, model_name="model"):
+        """a reference checkpoint -- path or dict, Lightning ('state_dict' -> 'model.xyz_encoder.params' ...) or already slimmed -- with
+        the key handling of utils.extract_model_state_dict (utils.py:4-18)"""
+        if not isinstance(ckpt, dict):
+            ckpt = torch.load(ckpt, map_location="cpu")
+        if "state_dict" in ckpt:
+            ckpt = ckpt["state_dict"]
+        sd = {k[len(model_name) + 1:]: v for k, v in ckpt.items() if k.startswith(model_name)}
+        for k in ("xyz_encoder.params", "rgb_net.params"):
+            if k not in sd:
+                raise KeyError(f"checkpoint has no '{model_name}.{k}'")
+        if sd["xyz_encoder.params"].numel() != self.n_xyz or sd["rgb_net.params"].numel() != self.n_rgb:
+            raise ValueError(f"checkpoint is for another configuration: xyz_encoder.params {sd['xyz_encoder.params'].numel()} (engine {self.n_xyz}), "
+                             f"rgb_net.params {sd['rgb_net.params'].numel()} (engine {self.n_rgb})")
+        self.load_state_dict({k: v.to(self.dev) for k, v in sd.items() if torch.is_tensor(v)})
+
     # ------------------------------------------------------------------------------------------------ field queries
     @torch.no_grad()
     def field(self, xyzs, dirs):

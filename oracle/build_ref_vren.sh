@@ -17,6 +17,11 @@ if [ ! -d "$REF/models/csrc" ]; then
   echo "[build_ref_vren] $REF not present (GPU box?) - using prebuilt files in $OUT"; exit 0
 fi
 mkdir -p "$OUT"
+# the frozen-API python layer, staged (git-ignored) so GPU-side integration tests can drive the
+# UNMODIFIED reference rendering/custom_functions/networks/losses/utils through our shims.
+mkdir -p "$OUT/refpy/models"
+cp "$REF/models/__init__.py" "$REF/models/custom_functions.py" "$REF/models/networks.py" "$REF/models/rendering.py" "$OUT/refpy/models/"
+cp "$REF/losses.py" "$REF/utils.py" "$OUT/refpy/"
 if ls "$OUT"/vren_ref*.so >/dev/null 2>&1 && [ -z "${FORCE:-}" ]; then
   echo "[build_ref_vren] already built: $(ls "$OUT"/vren_ref*.so)"; exit 0
 fi
@@ -27,10 +32,5 @@ sed -i -E 's/([A-Za-z_]+)\.type\(\), "/\1.scalar_type(), "/' *.cu
 sed -i -E "s/name='vren'/name='vren_ref'/g" setup.py
 TORCH_CUDA_ARCH_LIST="10.0" MAX_JOBS=${MAX_JOBS:-6} python setup.py build_ext --inplace > "$OUT/build.log" 2>&1
 cp vren_ref*.so "$OUT/"
-# the frozen-API python layer, staged (git-ignored) so GPU-side integration tests can drive the
-# UNMODIFIED reference rendering/custom_functions/networks/losses through our shims.
-mkdir -p "$OUT/refpy/models"
-cp "$REF/models/__init__.py" "$REF/models/custom_functions.py" "$REF/models/networks.py" "$REF/models/rendering.py" "$OUT/refpy/models/"
-cp "$REF/losses.py" "$OUT/refpy/"
 rm -rf "$SCRATCH"
 echo "[build_ref_vren] built $(ls "$OUT"/vren_ref*.so)"

@@ -373,3 +373,49 @@ def test_mixed_feature_grid_trains_and_renders():
     out = eng.render(o, d)                                  # dispatches to the per-op loop for shapes outside the fused kernels
     assert out["rgb"].shape == (256, 3) and torch.isfinite(out["rgb"]).all() and int(out["total_samples"]) > 0
     assert float((out["rgb"] - tgt).abs().mean()) < 0.25
+
+
+def test_checkpoint_round_trip_with_the_reference_loader(tmp_path):
+    """engine -> checkpoint file -> the reference's own utils.load_ckpt into the reference's NGP module (on our drop-ins): same field;
+    and a Lightning-style checkpoint of that module -> engine.load_checkpoint: same parameters, bit for bit"""
+    rendering, networks, _ = _load_reference_python()
+    sys.path.insert(0, REFPY)
+    try:
+        import utils as ref_utils
+    finally:
+        sys.path.remove(REFPY)
+    eng = _engine(256)
+    rays = scenes.scene("lego", 256, seed=14)
+    o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
+    tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).cuda().float()
+    for s in range(1, 20):
+        eng.train_step(o, d, tgt, global_step=s)
+    path = str(tmp_path / "epoch=0_slim.ckpt")
+    eng.save_checkpoint(path)
+    assert "model.density_grid" not in torch.load(path)["state_dict"]                      # slimmed like utils.slim_ckpt
+    model = networks.NGP(scale=0.5, hparams=_hparams(), rgb_act="Sigmoid").cuda()
+    ref_utils.load_ckpt(model, path)                                                       # the reference's loader, unmodified
+    assert torch.equal(model.xyz_encoder.params.detach(), eng.params[:eng.n_xyz]) and torch.equal(model.density_bitfield, eng.density_bitfield)
+    n = int(eng.counter[0])
+    x, dirs = eng.xyzs[:n].clone(), eng.dirs[:n].clone()
+    with torch.no_grad():
+        sig_r, rgb_r = model(x, dirs)
+    sig, rgb = eng.field(x, dirs)
+    torch.testing.assert_close(sig, sig_r.float(), rtol=1e-2, atol=1e-3)                   # fused kernel vs the module-by-module path: fp16 ulps
+    torch.testing.assert_close(rgb, rgb_r.float(), rtol=0, atol=3e-3)
+    # the other direction: what the reference's trainer writes
+    with torch.no_grad():
+        model.xyz_encoder.params.mul_(1.5); model.rgb_net.params.add_(0.01)
+    full = {"state_dict": {**{"model." + k: v.cpu() for k, v in model.state_dict().items()}, "directions": torch.zeros(4, 3), "val_lpips.x": torch.zeros(1)},
+            "epoch": 3}
+    p2 = str(tmp_path / "epoch=3.ckpt")
+    torch.save(full, p2)
+    eng2 = _engine(256)
+    eng2.load_checkpoint(p2)
+    assert torch.equal(eng2.params[:eng2.n_xyz], model.xyz_encoder.params.detach())
+    assert torch.equal(eng2.params[eng2.off_rgb:eng2.off_rgb + eng2.n_rgb], model.rgb_net.params.detach())
+    assert torch.equal(eng2.params_h, eng2.params.half()) and torch.equal(eng2.density_bitfield, model.density_bitfield)
+    with pytest.raises(ValueError):
+        _engine(256, T=14).load_checkpoint(p2)
+    with pytest.raises(KeyError):
+        eng2.load_checkpoint({"state_dict": {"model.rgb_net.params": torch.zeros(eng2.n_rgb)}})
