@@ -167,6 +167,7 @@ def algorithmic(name, n_samples, n_rays, n_params, rgb_flops):
         "grid_encode_fwd": ("hbm", 588.0 * n_samples), "grid_encode_bwd": ("hbm", 588.0 * n_samples),
         "march_count": ("hbm", 60.0 * n_rays + 8.0 * n_samples), "march_write": ("hbm", 24.0 * n_rays + 40.0 * n_samples),
         "composite_train_fw": ("hbm", 28.0 * n_samples + 52.0 * n_rays), "composite_train_bw": ("hbm", 48.0 * n_samples + 64.0 * n_rays),
+        "composite_loss_train": ("hbm", 64.0 * n_samples + 128.0 * n_rays),     # fw 28 B + second sweep 20 B read, 16 B written per sample
         "adam": ("hbm", 30.0 * n_params),
         "mlp_sigma_fwd": ("tensor", 6144.0 * n_samples), "mlp_rgb_fwd": ("tensor", rgb_flops * n_samples),
         "mlp_sigma_bwd": ("tensor", 2 * 6144.0 * n_samples), "mlp_rgb_bwd": ("tensor", 2 * rgb_flops * n_samples),
@@ -176,7 +177,7 @@ def algorithmic(name, n_samples, n_rays, n_params, rgb_flops):
 
 
 PROFILED = ["march_count", "march_scan", "march_write", "grid_encode_fwd", "mlp_sigma_fwd", "sh_sigma", "mlp_rgb_fwd", "field_fwd", "composite_train_fw",
-            "nerf_loss", "composite_train_bw", "prep_dout2", "mlp_rgb_bwd", "merge_dh", "mlp_sigma_bwd", "grid_encode_bwd", "field_bwd", "adam"]
+            "nerf_loss", "composite_train_bw", "composite_loss_train", "prep_dout2", "mlp_rgb_bwd", "merge_dh", "mlp_sigma_bwd", "grid_encode_bwd", "field_bwd", "adam"]
 
 
 def run_ours(args):

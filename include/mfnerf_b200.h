@@ -224,6 +224,10 @@ int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg_host, int64_t n_max, 
 /* 1 when this shape runs on the fused tcgen05 kernels (field_fused.cu), 0 when it runs on the unfused pipeline, <0 on a bad config.
  * The fused backward reads nothing but the workspace, dL_dsigmas and dL_drgbs: `xyzs` may already be overwritten when it runs. */
 int mfn_field_is_fused(const mfn_field_cfg* cfg_host);
+/* Fused shapes, training workspace: address (inside `workspace`) of the int32 where mfn_field_fwd leaves the sample count it used,
+ * min(*n_dev, n_max).  Pass it as `n_dev` to mfn_field_bwd when the caller's own counter may be overwritten in between (the engine
+ * starts marching the next batch while the backward pass of this one is still running).  NULL for shapes on the unfused pipeline. */
+void* mfn_field_count_ptr(const mfn_field_cfg* cfg_host, void* workspace, int64_t n_max);
 /* xyzs, dirs (n,3) f32 -> sigmas (n) f32, rgbs (n,3) f32 (values rounded to fp16 like tcnn's output) */
 int mfn_field_fwd(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, const float* dirs,
                   int64_t n_max, const int32_t* n_dev, float* sigmas, float* rgbs, void* workspace, int64_t workspace_bytes, void* stream);
@@ -269,6 +273,17 @@ int mfn_render_finish(float* rgb, const float* opacity, const float* bg_rgb_host
 int mfn_nerf_loss_fwbw(const float* rgb, const float* opacity, const float* target, const float* distortion, int64_t n_rays,
                        const float* bg_rgb_host, float lambda_opacity, float lambda_distortion, float grad_scale, float* dL_drgb,
                        float* dL_dopacity, float* dL_ddistortion, float* rgb_final, float* loss_out, void* stream);
+/* mfn_composite_train_fw + mfn_nerf_loss_fwbw (without distortion term) + mfn_composite_train_bw in ONE launch: the engine's training step
+ * when distortion_loss_w == 0 (VolumeRenderer.forward custom_functions.py:137-146 -> NeRFLoss losses.py:47-60 with the background blend of
+ * rendering.py:153-161 -> VolumeRenderer.backward :148-159).  Outputs as in the three calls (dL_drgb (n,3), dL_dopacity (n), rgb_final may be
+ * NULL); loss_out (3 floats, or NULL) is WRITTEN, not accumulated: {rgb term, opacity term, 0}.  scratch16: 16 zero-initialised bytes the
+ * call leaves zeroed.  clear_flag (or NULL): an int32 set to 0 at the end of the call -- the backward pass's overflow flag, cleared here so
+ * that the step needs no separate memset. */
+int mfn_composite_loss_train(const float* sigmas, const float* rgbs, const float* deltas, const float* ts, const int64_t* rays_a,
+                             const float* target, float T_threshold, int64_t n_rays, int64_t n_samples, const float* bg_rgb_host,
+                             float lambda_opacity, float grad_scale, int64_t* total_samples, float* opacity, float* depth, float* rgb,
+                             float* ws, float* rgb_final, float* dL_drgb, float* dL_dopacity, float* dL_dsigmas, float* dL_drgbs,
+                             float* loss_out, float* scratch16, int32_t* clear_flag, void* stream);
 /* replaces torch_scatter.segment_csr(src, indptr) (sum) in RayMarcher.backward (custom_functions.py:102-112):
  * src (rows, width) f32, indptr (n_segments+1) int64 -> out (n_segments, width) f32 */
 int mfn_segment_sum(const float* src, const int64_t* indptr, int64_t n_segments, int width, float* out, void* stream);

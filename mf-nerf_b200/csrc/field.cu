@@ -18,7 +18,7 @@ static bool use_fused(const mfn_field_cfg* c) {
 }
 
 // workspace of the fused path: [tile blobs | rgb copy (n,3) f32 | dfeats (n,32) f16 | weight-gradient partials]
-struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, total; };
+struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, count, total; };
 static FusedWs fused_ws(int64_t n, bool training) {
     FusedWs w{};
     size_t o = 0;
@@ -28,6 +28,7 @@ static FusedWs fused_ws(int64_t n, bool training) {
         w.dfeats = o; o += (size_t)((n + 63) / 64 * 64) * 64;
         w.partials = o; o += (fused_partial_bytes() + 255) / 256 * 256;
         w.x01 = o; o += (size_t)(n * 16 + 255) / 256 * 256;
+        w.count = o; o += 256;         // int32: the sample count of the forward pass (mfn_field_count_ptr)
     }
     w.total = o > 256 ? o : 256;
     return w;
@@ -147,6 +148,11 @@ extern "C" int mfn_field_is_fused(const mfn_field_cfg* cfg) {
     return use_fused(cfg) ? 1 : 0;
 }
 
+extern "C" void* mfn_field_count_ptr(const mfn_field_cfg* cfg, void* workspace, int64_t n_max) {
+    if (field_cfg_ok(cfg, "mfn_field_count_ptr") != MFN_OK || !workspace || n_max < 0 || !use_fused(cfg)) return nullptr;
+    return (char*)workspace + fused_ws(n_max, true).count;
+}
+
 extern "C" int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg, int64_t n_max, int training) {
     if (field_cfg_ok(cfg, "mfn_field_workspace_bytes") != MFN_OK || n_max < 0) return -1;
     const size_t v1 = field_ws(cfg, n_max, training != 0).total;
@@ -191,7 +197,7 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         const bool train = (size_t)workspace_bytes >= fw.total;
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
         f.sigmas = sigmas; f.rgbs = rgbs;
-        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.x01 = (float4*)(ws + fw.x01); }
+        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.x01 = (float4*)(ws + fw.x01); f.n_out = (int32_t*)(ws + fw.count); }
         { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
     }

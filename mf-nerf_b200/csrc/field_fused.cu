@@ -216,6 +216,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const int row = tid & (kFT - 1), hsel = tid >> 7;
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
+    if (MODE == 1 && a.n_out && blockIdx.x == 0 && tid == 0) *a.n_out = (int32_t)n;     // the backward pass's own copy of the count
     if ((int64_t)blockIdx.x >= n_tiles) return;      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
     stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE < 2);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }

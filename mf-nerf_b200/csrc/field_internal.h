@@ -73,6 +73,7 @@ struct FusedArgs {
     float* sigmas; float* rgbs;
     float* rgbs_copy;        // training: second copy of rgbs kept in the workspace for the backward pass
     __half* h_out;           // mode 3: (n, 16) fp16 raw outputs of the sigma network
+    int32_t* n_out;          // training: where the forward pass leaves min(*n_dev, n_max) for the backward pass (workspace)
     unsigned char* blobs;    // training: activation tiles, 64 KiB per 128 samples
     int rgb_act;
     // backward only

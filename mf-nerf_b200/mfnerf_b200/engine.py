@@ -119,7 +119,13 @@ class NGPEngine:
         self.field_ws = torch.empty(_lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), S, 1), dtype=torch.uint8, device=d)
         # fused field kernels: the backward pass reads only its workspace, so step t+1's marching front may overwrite the sample arrays
         # as soon as step t's compositor backward is done and overlap step t's field backward + scatter
-        self._deep = self.dp and _lib.lib.mfn_field_is_fused(ctypes.byref(self.cfg)) == 1
+        self._fused = _lib.lib.mfn_field_is_fused(ctypes.byref(self.cfg)) == 1
+        self._deep = self.dp and self._fused
+        # fused shapes without distortion loss: compositing forward + loss + compositing backward are ONE kernel, the field forward
+        # leaves its sample count in the workspace for the backward pass, and no copy / memset node is left in the step
+        self._fast_front = self._fused and self.distortion_w == 0
+        self._comp_scratch = torch.zeros(4, device=d)
+        self._n_back = ctypes.c_void_p(_lib.lib.mfn_field_count_ptr(ctypes.byref(self.cfg), ptr(self.field_ws), S)) if self._fused else None
         self._graph = None
         self._cells_ws = None
         self.graph_replays = 0
@@ -283,6 +289,14 @@ class NGPEngine:
         """field forward, compositing forward, loss, compositing backward: the last readers of the marcher's sample arrays"""
         d, st, R, S = self.dev, stream_ptr(self.dev), self.n_rays, self.cap
         cfg = ctypes.byref(self.cfg)
+        if self._fast_front:
+            call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), ptr(self.dirs), S, ptr(self.counter), ptr(self.sigmas),
+                 ptr(self.rgbs), ptr(self.field_ws), self.field_ws.numel(), st)
+            call("mfn_composite_loss_train", ptr(self.sigmas), ptr(self.rgbs), ptr(self.deltas), ptr(self.ts), ptr(self.rays_a), ptr(self.target), self.T_thr, R, S,
+                 self.bg, self.lambda_opacity, 1.0, ptr(self.total_samples), ptr(self.opacity), ptr(self.depth), ptr(self.rgb), ptr(self.ws), ptr(self.rgb_final),
+                 ptr(self.dL_drgb), ptr(self.dL_dopacity), ptr(self.dL_dsigmas), ptr(self.dL_drgbs), ptr(self.loss_terms), ptr(self._comp_scratch),
+                 ptr(self.overflow), st)
+            return
         self.n_field.copy_(self.counter[:1])
         n_dev = ptr(self.n_field)
         call("mfn_field_fwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), ptr(self.dirs), S, n_dev, ptr(self.sigmas),
@@ -308,8 +322,9 @@ class NGPEngine:
         """field backward (MLP dgrad / wgrad, hash-grid scatter) into self.grads"""
         st, S = stream_ptr(self.dev), self.cap
         cfg = ctypes.byref(self.cfg)
-        n_dev = ptr(self.n_field)
-        self.overflow.zero_()
+        n_dev = self._n_back if self._fast_front else ptr(self.n_field)
+        if not self._fast_front:          # (the fused compositing kernel of the front stage has cleared the flag)
+            self.overflow.zero_()
         call("mfn_field_bwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
              self.loss_scale, ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
 

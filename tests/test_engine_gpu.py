@@ -6,6 +6,7 @@
   * CUDA-graph replay == eager; training actually reduces the loss; test-time render vs the reference's __render_rays_test.
 Tolerances: fp16 field outputs rtol 2e-2 / atol 3e-3; per-ray rgb/opacity/depth atol 2e-3 (fp16 rgbs feed the compositor);
 parameter gradients: 8 % on entries above 5 % of the largest one (fp16 dZ rounding per layer), 3 % of the max elsewhere."""
+import ctypes
 import os
 import sys
 import types
@@ -419,3 +420,45 @@ def test_checkpoint_round_trip_with_the_reference_loader(tmp_path):
         _engine(256, T=14).load_checkpoint(p2)
     with pytest.raises(KeyError):
         eng2.load_checkpoint({"state_dict": {"model.rgb_net.params": torch.zeros(eng2.n_rgb)}})
+
+
+@pytest.mark.parametrize("name", ["lego", "unbounded"])
+def test_fused_composite_loss_kernel_equals_the_three_calls(name):
+    """mfn_composite_loss_train against mfn_composite_train_fw -> mfn_nerf_loss_fwbw -> mfn_composite_train_bw on the same samples
+    (dense enough for early termination, with empty rays): weights and termination indices exact, sums and gradients to rounding"""
+    import vren
+    from mfnerf_b200._lib import call, ptr, stream_ptr
+    R = 2048
+    sc = scenes.scene(name, R, seed=21)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    o, d, bits = T(sc["rays_o"]), T(sc["rays_d"]), T(sc["bitfield"])
+    _, ht, _ = vren.ray_aabb_intersect(o, d, T(sc["center"]), T(sc["half"]), 1)
+    h = T(scenes.near_clamp(ht.cpu().numpy()))
+    ra, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(o, d, h, bits, int(sc["cascades"]), float(sc["scale"]), float(sc["esf"]),
+                                                                 T(sc["noise"]), 128, 1024)
+    n = int(counter[0])
+    sig, rgbs = scenes.field_values(n, seed=22)
+    sig, rgbs = T(sig) * 4, T(rgbs)                       # denser: many rays terminate early
+    tgt = torch.rand(R, 3, device="cuda")
+    bg = (ctypes.c_float * 3)(1.0, 0.5, 0.25)
+    total, opacity, depth, rgb, ws = vren.composite_train_fw(sig, rgbs, deltas, ts, ra, 1e-4)
+    assert int((total < ra[:, 2]).sum()) > 20 and int((ra[:, 2] == 0).sum()) > 0
+    f = lambda *s: torch.full(s, 7.0, device="cuda")
+    g_rgb, g_op, fin, loss = f(R, 3), f(R), f(R, 3), torch.zeros(3, device="cuda")
+    call("mfn_nerf_loss_fwbw", ptr(rgb), ptr(opacity), ptr(tgt), None, R, bg, 1e-3, 0.0, 128.0, ptr(g_rgb), ptr(g_op), None, ptr(fin), ptr(loss), stream_ptr())
+    ds, dc = vren.composite_train_bw(g_op, torch.zeros(R, device="cuda"), g_rgb, torch.zeros(n, device="cuda"), sig, rgbs, ws, deltas, ts, ra, opacity, depth, rgb, 1e-4)
+    total2 = torch.zeros(R, dtype=torch.int64, device="cuda")
+    op2, de2, rgb2, ws2, fin2, g_rgb2, g_op2 = f(R), f(R), f(R, 3), f(n), f(R, 3), f(R, 3), f(R)
+    ds2, dc2, loss2 = f(n), f(n, 3), f(3)
+    scratch = torch.zeros(4, device="cuda"); flag = torch.ones(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):                                    # twice: the scratch must come back zeroed, the loss is written, not accumulated
+        call("mfn_composite_loss_train", ptr(sig), ptr(rgbs), ptr(deltas), ptr(ts), ptr(ra), ptr(tgt), 1e-4, R, n, bg, 1e-3, 128.0, ptr(total2), ptr(op2), ptr(de2),
+             ptr(rgb2), ptr(ws2), ptr(fin2), ptr(g_rgb2), ptr(g_op2), ptr(ds2), ptr(dc2), ptr(loss2), ptr(scratch), ptr(flag), stream_ptr())
+    assert torch.equal(total2, total) and torch.equal(ws2, ws) and int(flag[0]) == 0 and (scratch == 0).all()
+    for a, b in ((op2, opacity), (de2, depth), (rgb2, rgb), (fin2, fin)):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(g_rgb2, g_rgb, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(g_op2, g_op, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(dc2, dc, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(ds2, ds, rtol=1e-4, atol=1e-6 * float(ds.abs().max()))
+    torch.testing.assert_close(loss2, loss, rtol=1e-5, atol=1e-8)
