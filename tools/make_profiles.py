@@ -35,7 +35,7 @@ kn = hdr.index("Kernel Name"); rd = hdr.index("dram__bytes_read.sum"); wr = hdr.
 mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 samples = int(open("gpurun_out/ncu_step.log").read().split("samples")[-1].split()[0])
 names = {"field_fwd_fused": "field_fwd", "field_bwd_fused": "field_bwd", "grid_scatter_pair": "grid_encode_bwd", "march_count": "march_count", "march_scan_write": "march_write",
-         "composite_train_fw": "composite_train_fw", "composite_train_bw": "composite_train_bw", "adam_kernel": "adam", "nerf_loss": "nerf_loss", "reduce_wgrad": "reduce_wgrad",
+         "composite_train_fw": "composite_train_fw", "composite_train_bw": "composite_train_bw", "composite_loss_train": "composite_loss_train", "adam_kernel": "adam", "nerf_loss": "nerf_loss", "reduce_wgrad": "reduce_wgrad",
          "ray_setup": "ray_setup"}
 res = {"_source": "ncu --set full --clock-control none, one eager training step of the bench workload (tools/prof_step.py)", "_samples": samples}
 for r in rows[2:]:
