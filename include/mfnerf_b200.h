@@ -295,6 +295,11 @@ int mfn_clamp_near(float* hits_t, int64_t n_rays, float near_distance, void* str
  * may be NULL) refreshed; grads zeroed afterwards when zero_grad != 0.  `step` is 1-based. */
 int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
+/* the same step with its per-step scalars in DEVICE memory, hyper_dev = {lr, 1 - beta1^step, 1 - beta2^step} (fill a host copy with
+ * mfn_adam_hyper and upload it ahead of time): nothing in the launch changes from step to step, so it can be part of a CUDA graph. */
+int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host);
+int mfn_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* hyper_dev,
+                      float beta1, float beta2, float eps, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
 int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 
 #ifdef __cplusplus

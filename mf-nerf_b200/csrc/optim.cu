@@ -11,7 +11,9 @@ namespace mfn {
 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, __half* __restrict__ p_h, int64_t n,
-            float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale, const int32_t* __restrict__ skip_flag, int zero_grad) {
+            float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale, const int32_t* __restrict__ skip_flag, int zero_grad,
+            const float* __restrict__ hyper) {
+    if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }      // per-step scalars from device memory: the launch can live in a CUDA graph
     const bool skip = skip_flag && *skip_flag != 0;
     const uint64_t pol_keep = umma::policy_evict_last();   // the fp16 shadow (hash table + weights) is what the next step gathers from: keep it in L2
     const int64_t n4 = n / 4;
@@ -59,15 +61,37 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __res
 
 using namespace mfn;
 
+static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
+
+extern "C" int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host) {
+    if (step < 1 || !hyper_host) { set_error("mfn_adam_hyper: bad argument"); return MFN_ERR_ARG; }
+    hyper_host[0] = lr; hyper_host[1] = 1.f - powf(beta1, (float)step); hyper_host[2] = 1.f - powf(beta2, (float)step);
+    return MFN_OK;
+}
+
+extern "C" int mfn_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* hyper_dev,
+                                 float beta1, float beta2, float eps, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream) {
+    if (!hyper_dev) { set_error("mfn_adam_step_dev: null pointer"); return MFN_ERR_ARG; }
+    return adam_launch(params, grads, exp_avg, exp_avg_sq, params_h, n, 0.f, beta1, beta2, eps, 1.f, 1.f, hyper_dev, grad_scale, skip_flag, zero_grad, stream);
+}
+
 extern "C" int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1,
                              float beta2, float eps, int step, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream) {
-    if (n < 0 || step < 1) { set_error("mfn_adam_step: bad argument"); return MFN_ERR_ARG; }
+    if (step < 1) { set_error("mfn_adam_step: bad argument"); return MFN_ERR_ARG; }
+    float h[3];
+    mfn_adam_hyper(lr, beta1, beta2, step, h);
+    return adam_launch(params, grads, exp_avg, exp_avg_sq, params_h, n, h[0], beta1, beta2, eps, h[1], h[2], nullptr, grad_scale, skip_flag, zero_grad, stream);
+}
+
+static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream) {
+    if (n < 0) { set_error("mfn_adam_step: bad argument"); return MFN_ERR_ARG; }
     if (n == 0) return MFN_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("mfn_adam_step: null pointer"); return MFN_ERR_ARG; }
     if ((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) || ((uintptr_t)params_h & 7)) {
         set_error("mfn_adam_step: buffers must be 16-byte aligned"); return MFN_ERR_ARG;
     }
-    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
     int64_t blocks = ceil_div(n / 4 + 1, 256);
     static int per_sm = 0;
     if (per_sm == 0) { const char* e = getenv("MFN_ADAM_BPS"); per_sm = e ? atoi(e) : 32; if (per_sm < 1) per_sm = 32; }      // measured: 8 -> 75 us, 16 -> 64 us, 32 -> 63 us (11.4 M params)
@@ -75,7 +99,7 @@ extern "C" int mfn_adam_step(float* params, float* grads, float* exp_avg, float*
     if (blocks > cap) blocks = cap;
     ProfScope ps("adam", (cudaStream_t)stream);
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_h, n, lr, beta1, beta2, eps, bc1,
-                                                                    bc2, grad_scale, skip_flag, zero_grad);
+                                                                    bc2, grad_scale, skip_flag, zero_grad, hyper);
     return check_launch("mfn_adam_step", (cudaStream_t)stream);
 }
 

@@ -104,6 +104,7 @@ class NGPEngine:
         self.dist_loss, self.dL_ddist = f(R), f(R)
         self.loss_terms = torch.zeros(3, device=d)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
+        self._adam_hyper = torch.zeros(4, device=d)              # {lr, 1 - beta1^t, 1 - beta2^t}: the optimiser's per-step scalars when it runs inside a graph
         self.center = torch.zeros(1, 3, device=d); self.half_size = torch.full((1, 3), self.scale, device=d)
         # per-sample buffers at fixed capacity
         self.cap = int(sample_capacity) if sample_capacity else R * MAX_SAMPLES
@@ -334,6 +335,29 @@ class NGPEngine:
              float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 1,
              stream_ptr(self.dev))
 
+    def _adam_from_device_scalars(self, st):
+        call("mfn_adam_step_dev", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
+             ptr(self._adam_hyper), 0.9, 0.999, 1e-15, mdist.grad_scale(self.loss_scale, 1), ptr(self.overflow), 1, st)
+
+    def _upload_adam_scalars(self, lr, stream):
+        """{lr, 1 - beta1^t, 1 - beta2^t} of the step being enqueued -> device memory, through a ring of pinned rows, on `stream` (the back
+        stream, where it queues behind the previous step's optimiser and ahead of this step's backward: off the critical path)"""
+        if not hasattr(self, "_hyper_host"):
+            self._hyper_host = torch.zeros(16, 4).pin_memory()
+            self._hyper_evt = [torch.cuda.Event() for _ in range(16)]
+            self._hyper_used = [False] * 16
+            self._hyper_k = 0
+        k = self._hyper_k % 16
+        self._hyper_k += 1
+        if self._hyper_used[k]:
+            self._hyper_evt[k].synchronize()      # 16 steps ago: long done unless the host is that far ahead
+        row = self._hyper_host[k]
+        _lib.check(_lib.lib.mfn_adam_hyper(float(lr), 0.9, 0.999, int(self.step_count), ctypes.c_void_p(row.data_ptr())), "mfn_adam_hyper")
+        with torch.cuda.stream(stream):
+            self._adam_hyper.copy_(row, non_blocking=True)
+            self._hyper_evt[k].record(stream)
+        self._hyper_used[k] = True
+
     def capture(self):
         """capture _forward_backward into a CUDA graph (call after at least one eager step)"""
         torch.cuda.synchronize(self.dev)
@@ -354,13 +378,21 @@ class NGPEngine:
                 self._field_front()
             with torch.cuda.graph(gc):
                 self._field_back()
+                if not self.collectives:      # one GPU: the optimiser is the last node of the back graph (its scalars come from device memory)
+                    self._adam_from_device_scalars(stream_ptr(self.dev))
             self._graph_march, self._graph, self._graph_back = ga, gb, gc
+            self._graph_back_only = gc
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._forward_backward()
             self._graph = g
         self.launches_per_forward_backward = int(_lib.lib.mfn_launch_count() - l0)
+        if self.dp and not self.collectives:      # the backward pass alone, without the optimiser node (replay_forward_backward)
+            gd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gd):
+                self._field_back()
+            self._graph_back_only = gd
         self.grads.zero_()
 
     def train_step(self, rays_o=None, rays_d=None, target=None, lr=None, global_step=None):
@@ -383,7 +415,7 @@ class NGPEngine:
         """replays everything capture() recorded, in order, on the current stream (tests; the training steps replay the pieces on
         their own streams)"""
         if self.dp:
-            self._graph_march.replay(); self._graph.replay(); self._graph_back.replay()
+            self._graph_march.replay(); self._graph.replay(); self._graph_back_only.replay()
         else:
             self._graph.replay()
 
@@ -561,20 +593,20 @@ class NGPEngine:
             self._field_front()
         self._cb_done.record(main)
         self.step_count += 1
-        cs.wait_event(self._cb_done)
         p_, g_, m_, v_, ph_ = self._adam_ptrs
         lr_ = float(self.lr if lr is None else lr)
+        if not self.collectives:
+            self._upload_adam_scalars(lr_, cs)
+        cs.wait_event(self._cb_done)
         with torch.cuda.stream(cs):
             if self._graph is not None:
-                self._graph_back.replay()
+                self._graph_back.replay()          # one GPU: ends with the optimiser (whole vector, gradient buffer zeroed by it)
             else:
                 self._field_back()
+                if not self.collectives:
+                    self._adam_from_device_scalars(self._comm_stream_ptr)
             if self.collectives:
                 self._back_done.record(cs); self._back_pending = True
-            if not self.collectives:       # one GPU: the whole vector, gradient buffer zeroed by the optimiser
-                call("mfn_adam_step", p_, g_, m_, v_, ph_, self.n_params, lr_, 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, 1),
-                     ptr(self.overflow), 1, self._comm_stream_ptr)
-            else:
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
                 torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
                 call("mfn_adam_step", p_, g_, m_, v_, ph_, self._shard, lr_, 0.9, 0.999, 1e-15, self.step_count,
