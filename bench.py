@@ -259,6 +259,7 @@ def run_ours(args):
         for i in range(K):
             step_from(pool, i if with_loss_readback else None)
         t_cpu = time.perf_counter() - t_cpu
+        eng.flush()        # the timing stream waits for the last step's backward pass, optimiser and loss read-back on the engine's streams
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)

@@ -546,6 +546,12 @@ class NGPEngine:
             torch.cuda.current_stream(self.dev).wait_event(self._loss_read)
             self._loss_read_pending = False
 
+    def flush(self):
+        """the current stream waits for everything the engine still has in flight on its own streams (the last step's backward pass,
+        optimiser and loss read-back): call before timing or reading results produced by train_step_packed / train_step_resident"""
+        self._wait_comm()
+        self._wait_loss_read()
+
     def _wait_comm(self):
         if getattr(self, "_comm_pending", False):
             torch.cuda.current_stream(self.dev).wait_event(self._comm_done)
