@@ -53,6 +53,9 @@ __host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
     return x;
 }
 
+// uniform integer in [0, n), n < 2^32, from the high 32 bits of a 64-bit random word (32 x 32 -> 64-bit product: cannot overflow)
+__host__ __device__ __forceinline__ uint32_t uniform_below(uint64_t r, uint32_t n) { return (uint32_t)(((r >> 32) * (uint64_t)n) >> 32); }
+
 // ---- warp helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -57,10 +57,10 @@ __global__ void grid_draw_occupied_kernel(const int32_t* __restrict__ cs, int64_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t r = splitmix64(seed ^ (uint64_t)i * 0xA24BAED4963EE407ull);
         if (total <= 0) {      // no occupied cell yet (the reference then adds no second half, l.188): spend the draws on uniform cells
-            idx_out[i] = (int32_t)(((r >> 11) * (uint64_t)n_cells) >> 53);
+            idx_out[i] = (int32_t)uniform_below(r, (uint32_t)n_cells);
             continue;
         }
-        const int32_t k = (int32_t)(((r >> 11) * (uint64_t)total) >> 53);     // uniform in [0, total)
+        const int32_t k = (int32_t)uniform_below(r, (uint32_t)total);     // uniform in [0, total)
         int64_t lo = 0, hi = n_cells - 1;                  // smallest j with cs[j] > k
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;

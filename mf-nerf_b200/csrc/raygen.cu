@@ -41,13 +41,13 @@ __global__ void __launch_bounds__(256) ray_batch_kernel(const __grid_constant__ 
     const uint64_t call = a.call_counter ? (uint64_t)*a.call_counter : 0ull;
     const uint64_t key = rg_splitmix64(a.seed ^ (call * 0xD6E8FEB86659FD93ull));
     // draw == 2 (ray_sampling_strategy 'same_image', base.py:26-27): one image for the whole batch
-    const int64_t shared_img = (int64_t)(((rg_splitmix64(key ^ 0x5851F42D4C957F2Dull) >> 11) * (uint64_t)a.n_images) >> 53);
+    const int64_t shared_img = (int64_t)uniform_below(rg_splitmix64(key ^ 0x5851F42D4C957F2Dull), (uint32_t)a.n_images);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         int64_t img, pix;
         if (a.draw) {
             const uint64_t r0 = rg_splitmix64(key ^ ((uint64_t)i * 0xD1342543DE82EF95ull)), r1 = rg_splitmix64(r0);
-            img = a.draw == 2 ? shared_img : (int64_t)(((r0 >> 11) * (uint64_t)a.n_images) >> 53);      // uniform in [0, n_images)
-            pix = (int64_t)(((r1 >> 11) * (uint64_t)a.n_pix) >> 53);                                    // uniform in [0, n_pix)
+            img = a.draw == 2 ? shared_img : (int64_t)uniform_below(r0, (uint32_t)a.n_images);      // uniform in [0, n_images)
+            pix = (int64_t)uniform_below(r1, (uint32_t)a.n_pix);                                        // uniform in [0, n_pix)
         } else {
             img = a.img_idxs ? a.img_idxs[i] : (int64_t)a.image;
             pix = a.pix_idxs ? a.pix_idxs[i] : i;

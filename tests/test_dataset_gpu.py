@@ -74,6 +74,13 @@ def test_ray_batch_draws_are_uniform_and_counter_based():
         assert abs(chi2 - (k - 1)) < 6 * (2 * (k - 1)) ** 0.5, (k, chi2)
     joint = img * (W * H) + pix                                                   # image and pixel are independent
     assert abs(float(torch.corrcoef(torch.stack([img.double(), pix.double()]))[0, 1])) < 0.01 and joint.unique().numel() > 0.5 * N * W * H
+    # a full-size image (640 000 pixels: the draw must not wrap in 64-bit arithmetic) -- coarse histogram over the whole index range
+    big = mds.Camera.from_K(K, (800, 800))
+    _, _, _, bi, bp = mds.ray_batch(big, poses, n, strategy="all_images", seed=5, call_counter=ctr, return_indices=True)
+    assert int(bp.max()) > 0.999 * 640000 and int(bp.min()) < 0.001 * 640000
+    h = torch.bincount(bp * 64 // 640000, minlength=64).double()
+    chi2 = float(((h - n / 64) ** 2 / (n / 64)).sum())
+    assert abs(chi2 - 63) < 6 * (2 * 63) ** 0.5, chi2
     # same (seed, counter) -> same batch; another counter value or seed -> another batch
     same = mds.ray_batch(cam, poses, n, strategy="all_images", seed=11, call_counter=ctr, return_indices=True)
     assert torch.equal(same[3], img) and torch.equal(same[4], pix)
@@ -183,3 +190,35 @@ def test_train_step_resident_draws_from_the_dataset():
     assert np.isfinite(losses).all() and np.mean(losses[-10:]) < 0.7 * np.mean(losses[:5]), (losses[:5], losses[-10:])
     full = ds.view_rays(3)
     assert full[0].shape == (W * H, 3) and torch.equal(full[2], ds.pixels[3, :, :3])
+
+
+def test_occupied_cell_draw_is_uniform_over_all_occupied_cells():
+    """mfn_grid_draw_occupied (networks.py:186-193: indices2[randint(len(indices2), (M,))]) on a full-size cascade: every occupied cell is
+    equally likely -- the k-th occupied cell for k uniform in [0, total), total far above 2^11 (a 64-bit product in the draw used to wrap)"""
+    from mfnerf_b200._lib import call, ptr, stream_ptr
+    G3 = 128 ** 3
+    g = torch.Generator(device="cuda").manual_seed(0)
+    occ = torch.rand(G3, device="cuda", generator=g) < 0.06
+    occ[: G3 // 8] = False                                        # an empty stretch at the start, like a carved grid
+    cs = torch.cumsum(occ.int(), 0, dtype=torch.int32)
+    total = int(cs[-1])
+    assert total > 100_000
+    n = 1 << 19
+    idx = torch.empty(n, dtype=torch.int32, device="cuda")
+    call("mfn_grid_draw_occupied", ptr(cs), G3, n, 1234, ptr(idx), stream_ptr())
+    idx = idx.long()
+    assert bool(occ[idx].all())
+    rank = cs[idx].long() - 1                                     # which occupied cell, 0 .. total-1
+    assert int(rank.max()) > 0.999 * total and int(rank.min()) < 0.001 * total
+    h = torch.bincount(rank * 64 // total, minlength=64).double()
+    chi2 = float(((h - n / 64) ** 2 / (n / 64)).sum())
+    assert abs(chi2 - 63) < 6 * (2 * 63) ** 0.5, chi2
+    # no occupied cell: uniform over all cells
+    zero = torch.zeros(G3, dtype=torch.int32, device="cuda")
+    idx2 = torch.empty(n, dtype=torch.int32, device="cuda")
+    call("mfn_grid_draw_occupied", ptr(zero), G3, n, 99, ptr(idx2), stream_ptr())
+    idx2 = idx2.long()
+    assert int(idx2.max()) > 0.999 * G3 and int(idx2.min()) < 0.001 * G3
+    h = torch.bincount(idx2 * 64 // G3, minlength=64).double()
+    chi2 = float(((h - n / 64) ** 2 / (n / 64)).sum())
+    assert abs(chi2 - 63) < 6 * (2 * 63) ** 0.5, chi2
