@@ -66,7 +66,8 @@ static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_a
 
 extern "C" int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host) {
     if (step < 1 || !hyper_host) { set_error("mfn_adam_hyper: bad argument"); return MFN_ERR_ARG; }
-    hyper_host[0] = lr; hyper_host[1] = 1.f - powf(beta1, (float)step); hyper_host[2] = 1.f - powf(beta2, (float)step);
+    // bias corrections evaluated in double from the float betas, like apex's multi_tensor_adam (1 - std::pow(float beta, int step))
+    hyper_host[0] = lr; hyper_host[1] = (float)(1.0 - pow((double)beta1, (double)step)); hyper_host[2] = (float)(1.0 - pow((double)beta2, (double)step));
     return MFN_OK;
 }
 

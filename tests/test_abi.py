@@ -78,3 +78,32 @@ def test_render_and_field_entry_points_validate_arguments():
     assert rb(cam, 0, 16) == -2 and rb(cam, 4, 16, draw=3) == -2 and rb(Camera(0.0, 1.0, 0.0, 0.0, 8, 8), 4, 16) == -2
     assert lib.mfn_grid_mark_invisible(None, None, 4, 64, 48, 1, 0.5, 128, 0.01, None, None, None) == -2
     assert lib.mfn_grid_mark_invisible(None, None, 0, 64, 48, 1, 0.5, 128, 0.01, None, None, None) == -2 and b"bad argument" in lib.mfn_last_error()
+
+
+def test_host_side_helpers_and_new_entry_points_validate_arguments():
+    """mfn_adam_hyper is pure host code; the fused step entry points reject null pointers before touching CUDA"""
+    import numpy as np
+    from mfnerf_b200 import _lib
+    from mfnerf_b200.engine import make_field_cfg
+    lib = _lib.lib
+    h = (ctypes.c_float * 4)()
+    for step in (1, 2, 17, 1000, 30000):
+        assert lib.mfn_adam_hyper(1e-2, 0.9, 0.999, step, h) == 0
+        assert h[0] == np.float32(1e-2)
+        b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))                                     # the betas are floats; the powers are taken in double (apex)
+        assert h[1] == np.float32(1 - b1 ** step) and h[2] == np.float32(1 - b2 ** step)
+    assert lib.mfn_adam_hyper(1e-2, 0.9, 0.999, 0, h) == -2 and lib.mfn_adam_hyper(1e-2, 0.9, 0.999, 1, None) == -2
+    assert lib.mfn_adam_step_dev(None, None, None, None, None, 16, None, 0.9, 0.999, 1e-15, 1.0, None, 1, None) == -2
+    assert lib.mfn_adam_step(None, None, None, None, None, 0, 1e-2, 0.9, 0.999, 1e-15, 1, 1.0, None, 1, None) == 0          # no parameters: no-op
+    bg = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
+    args = [None] * 6 + [1e-4, 16, 100, bg, 1e-3, 1.0] + [None] * 13 + [None]
+    assert lib.mfn_composite_loss_train(*args) == -2 and b"mfn_composite_loss_train" in lib.mfn_last_error()
+    args[7] = 0
+    assert lib.mfn_composite_loss_train(*args) == 0                                                                       # no rays: no-op
+    cfg = make_field_cfg(0.5)
+    assert lib.mfn_field_count_ptr(ctypes.byref(cfg), None, 1024) is None
+    fake = ctypes.c_void_p(1 << 20)                                                                                         # only address arithmetic happens
+    p = lib.mfn_field_count_ptr(ctypes.byref(cfg), fake, 1024)
+    assert p is not None and (1 << 20) < p < (1 << 20) + lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1024, 1)
+    wide = make_field_cfg(0.5, rgb_channels=128)
+    assert lib.mfn_field_count_ptr(ctypes.byref(wide), fake, 1024) is None                                                # unfused shapes keep no count
