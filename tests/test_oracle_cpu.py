@@ -173,3 +173,33 @@ def test_dataset_oracle_pinned_to_reference_python():
     assert fragile.mean() < 0.02
     assert np.array_equal(dens[~fragile], g["mi_density"][~fragile]) and np.array_equal(cnt[~fragile], g["mi_count"][~fragile])
     assert (dens != g["mi_density"]).sum() <= 2                                                   # here they agree everywhere; fragile cells may flip
+
+
+def test_mixed_feature_index_transformation_properties():
+    """the MixedFeature spec (include/mfnerf_b200.h) as restated in oracle/field_ref.py: K tables of 2^T entries, level l
+    in table l*K/L, vertices of a level map to DISTINCT vertices of the table's canonical (finest) grid, in order, and the canonical
+    level maps onto itself"""
+    import torch
+    from oracle import field_ref as fr
+    for scale, L, K, T in ((0.5, 16, 8, 20), (16.0, 16, 4, 22), (0.5, 16, 1, 19), (0.5, 8, 8, 16)):
+        b = float(np.exp(np.log(2048 * scale / 16) / (L - 1)))
+        levels, total = fr.grid_layout(L, 2, T, 16, b, "MixedFeature", K)
+        assert total == K << T
+        for l, lv in enumerate(levels):
+            k = l * K // L
+            assert lv["offset"] == k << T and lv["entries"] == 1 << T and lv["hashed"]
+            group = [j for j in range(L) if j * K // L == k]
+            canon = levels[group[-1]]
+            v = torch.arange(0, lv["res"] + 1)
+            c = fr._canon(v, lv["canon"])
+            if l == group[-1]:
+                assert lv["canon"] == 1.0 and torch.equal(c, v)
+            else:
+                assert lv["canon"] > 1.0 and bool((c[1:] > c[:-1]).all())          # injective and monotone
+            # (vertex 0 sits half a cell outside the unit cube, at x = -0.5 / scale_l: its canonical coordinate may be negative; kernel and
+            #  restatement both hash it in two's-complement uint32 arithmetic)
+            assert int(c.min()) >= -int(lv["canon"]) - 1 and int(c.max()) <= canon["res"] + 2 * lv["canon"] + 2
+            # nearest canonical vertex of the level vertex's position x = (v - 0.5) / scale_l
+            x = (v.double() - 0.5) / lv["scale"]
+            nearest = torch.floor(x * canon["scale"] + 0.5 + 0.5).long()
+            assert int((c - nearest).abs().max()) <= 1 and float((c == nearest).double().mean()) > 0.99
