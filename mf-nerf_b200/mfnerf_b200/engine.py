@@ -442,8 +442,10 @@ class NGPEngine:
 
     # ------------------------------------------------------------------------------------------------ resident data set
     def attach_dataset(self, dataset, seed=0):
-        """`dataset`: mfnerf_b200.dataset.ResidentDataset.  train_step_resident() then draws its own batches on the device."""
-        self.dataset, self._batch_seed = dataset, int(seed)
+        """`dataset`: mfnerf_b200.dataset.ResidentDataset.  train_step_resident() then draws its own batches on the device.
+        Data-parallel: every rank holds the data set and draws its OWN rays (the reference's per-rank sampling, datasets/base.py:22-44)."""
+        rank = torch.distributed.get_rank(self.pg) if self.world_size > 1 else 0
+        self.dataset, self._batch_seed = dataset, mdist.shard_seed(seed, rank)
 
     def _draw_batch(self):
         """one launch: random (image, pixel) per ray -> rays_o, rays_d, target straight into the step's static buffers
