@@ -185,6 +185,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from mfnerf_b200 import _lib
+    from mfnerf_b200 import dist as mdist
     from mfnerf_b200 import synthetic as syn
     from mfnerf_b200.engine import NGPEngine
 
@@ -235,9 +236,10 @@ def run_ours(args):
     # host warm-up: on a fresh box the first second of stepping is host-bound (libcuda / interpreter pages still faulting in: ~0.4 ms
     # of launch work per step instead of ~0.13 ms), which would be charged to the first timed region.  Keep stepping, untimed, for
     # 1.5 s of wall time; every timed region restarts from the snapshot taken BEFORE it (same workload as without it).
-    t_warm, extra_warmup = time.perf_counter(), 0
-    while time.perf_counter() - t_warm < 1.5:
-        step_from(pool_dev); extra_warmup += 1
+    # Every step enqueues collectives when world > 1, so the NUMBER of steps must be identical on every rank: the wall clock only
+    # decides between chunks, and the decision is rank 0's, broadcast to the others (a per-rank clock would let ranks issue different
+    # numbers of reduce-scatters and dead-lock the job -- round 1's SCALE failure).
+    extra_warmup = mdist.agreed_warmup(lambda: step_from(pool_dev), world, dev, seconds=1.5, chunk=128, max_chunks=64)
     torch.cuda.synchronize(dev)
 
     def rewind():
@@ -347,7 +349,6 @@ def run_ours(args):
     #      (mfnerf_b200.dist.tile_rows, no collective); a frame's time is its slowest rank's
     render = None
     if not args.no_render:
-        from mfnerf_b200 import dist as mdist
         pose = syn.camera_poses(4, seed=7)
         row0, row1 = mdist.tile_rows(800, rank, world)
         frames, out = [], None

@@ -4,6 +4,7 @@ all-reduce of the flat gradient per training step, image row tiles at test time 
 Nothing here touches CUDA directly, so the same code runs under `gloo` on CPU tensors (tests/test_multi_cpu.py) and under
 `nccl` on the GPUs (engine.py, bench.py)."""
 import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -63,3 +64,25 @@ def sum_over_ranks(value, device, world_size, group=None):
     t = torch.tensor([float(value)], device=device, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return float(t.item())
+
+
+def agreed_warmup(step, world_size, device, seconds, chunk=128, max_chunks=64, group=None, clock=time.perf_counter, sync=None):
+    """Untimed host warm-up whose LENGTH is the same on every rank: `step()` runs in chunks of `chunk`; after each chunk rank 0's
+    clock decides whether `seconds` have passed and the decision is broadcast.  Every training step enqueues collectives when
+    world_size > 1, so a per-rank wall-clock loop would let the ranks issue different numbers of them and dead-lock (bench.py,
+    round 1).  Returns the number of steps run."""
+    t0, n = clock(), 0
+    for _ in range(int(max_chunks)):
+        for _ in range(int(chunk)):
+            step()
+        n += int(chunk)
+        if sync is not None:
+            sync()
+        stop = (clock() - t0) >= seconds
+        if world_size > 1:
+            t = torch.tensor([1 if stop else 0], device=device, dtype=torch.int32)
+            dist.broadcast(t, src=0, group=group)
+            stop = bool(int(t.item()))
+        if stop:
+            break
+    return n

@@ -399,13 +399,13 @@ class NGPEngine:
         """one reference training_step (train.py:164-190).  Inputs (device tensors) are copied into the engine's static buffers."""
         if global_step is None:
             global_step = self.step_count
-        if global_step % 16 == 0:                                                            # train.py:165-168
-            self.update_density_grid(warmup=global_step < 256)
-        if self.dp:
+        if self.dp:                # (_step_dp runs the occupancy update itself, on the march stream: exactly one update per 16 steps)
             self._step_dp(lambda: (self.rays_o.copy_(rays_o, non_blocking=True), self.rays_d.copy_(rays_d, non_blocking=True),
                                    self.target.copy_(target, non_blocking=True)) if rays_o is not None else None, lr, global_step)
             self._wait_comm()      # callers of train_step may read the parameters right away; train_step_packed leaves the optimiser in flight
             return
+        if global_step % 16 == 0:                                                            # train.py:165-168
+            self.update_density_grid(warmup=global_step < 256)
         if rays_o is not None:
             self.rays_o.copy_(rays_o, non_blocking=True); self.rays_d.copy_(rays_d, non_blocking=True); self.target.copy_(target, non_blocking=True)
         self._run_forward_backward()

@@ -35,18 +35,22 @@ def _init_mlp(params, in_dim, width, n_hidden, n_out_padded, gen):
 
 
 class _ParamCache:
-    """fp16 shadow of the fp32 master parameters, refreshed when the Parameter is modified (optimizer.step)"""
+    """fp16 shadow of the fp32 master parameters, re-cast on EVERY forward (one cast kernel, ~11 us for the 11.4 M parameters of
+    the Lego configuration).  It must not be keyed on `Parameter._version`: the reference trainer's optimiser is apex FusedAdam
+    (train.py:23,136), which updates `p.data` through raw pointers and never bumps the version counter -- a version-keyed cache
+    would keep serving the initial weights while the fp32 masters drift.  Grad-enabled forwards get a fresh tensor (autograd saves
+    it for backward); no-grad forwards (NGP.density in update_density_grid, the test-time render loop) reuse one buffer."""
 
     def __init__(self):
-        self._key = None
-        self._half = None
+        self._buf = None
 
     def get(self, p):
-        key = (p.data_ptr(), p._version, p.device)
-        if key != self._key:
-            self._half = p.detach().to(torch.float16)
-            self._key = key
-        return self._half
+        if torch.is_grad_enabled() and p.requires_grad:
+            return p.detach().to(torch.float16)
+        if self._buf is None or self._buf.shape != p.shape or self._buf.device != p.device:
+            self._buf = torch.empty_like(p, dtype=torch.float16)
+        self._buf.copy_(p.detach())
+        return self._buf
 
 
 def _parse_network(cfg):

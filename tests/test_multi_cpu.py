@@ -102,3 +102,56 @@ def test_reference_arm_runs_on_rank0_only():
     line = json.loads(outs[0].splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "train_rays_per_sec" and line["n_gpus"] == 2
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+WARMUP_WORKER = r'''
+import os, sys, json, time
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "mf-nerf_b200"))
+from mfnerf_b200 import dist as mdist
+rank, local, world = mdist.env_world()
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+# a stub of bench.py's loop structure: every "training step" enqueues the collectives of engine._step_dp (reduce-scatter, flag
+# all-reduce, all-gather); the ranks' clocks run at very different speeds (rank 1's is 5x faster and it is a slower stepper)
+calls = dict(n=0)
+g = torch.ones(8); shard = torch.zeros(8 // world); flag = torch.zeros(1, dtype=torch.int32); full = torch.zeros(8)
+def step():
+    calls["n"] += 1
+    dist.all_reduce(g); dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    dist.all_gather_into_tensor(full, shard)
+    g.fill_(1.0)
+    if rank == 1:
+        time.sleep(0.0005)
+t0 = time.perf_counter()
+clock = (lambda: time.perf_counter()) if rank == 0 else (lambda: t0 + 5.0 * (time.perf_counter() - t0))
+n = mdist.agreed_warmup(step, world, "cpu", seconds=0.15, chunk=16, max_chunks=1000, clock=clock)
+dist.barrier()      # would mis-pair with a straggler's all_reduce (and hang) if the counts differed
+print(json.dumps(dict(rank=rank, n=n, calls=calls["n"])))
+dist.destroy_process_group()
+'''
+
+
+def test_untimed_warmup_runs_the_same_number_of_steps_on_every_rank(tmp_path):
+    """round 1's SCALE failure: a per-rank wall-clock warm-up loop let the ranks issue different numbers of collectives"""
+    port = _free_port()
+    script = tmp_path / "warm.py"
+    script.write_text(WARMUP_WORKER.format(root=ROOT, port=port))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    res = [json.loads(o[0].strip().splitlines()[-1]) for o in outs]
+    assert res[0]["n"] == res[1]["n"] == res[0]["calls"] == res[1]["calls"] > 0
+    assert res[0]["n"] % 16 == 0
+
+
+def test_bench_has_no_rank_local_wall_clock_loop_around_collectives():
+    """static guard: the only `while ... perf_counter()` loops in bench.py are in the CPU reference arm (no collectives there)"""
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    ours = src[src.index("def run_ours"):src.index("def main")]
+    assert not re.search(r"while[^\n]*perf_counter", ours)
+    assert "agreed_warmup" in ours

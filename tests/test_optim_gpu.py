@@ -1,5 +1,4 @@
-"""(file name sorts last on purpose: written when the round's GPU budget was spent, so a surprise here cannot hide the other parity tests
-from `pytest -x`.)  SURVEY 8f-1: the fused optimiser (mfn_adam_step / mfn_adam_step_dev) against a float64 restatement of apex FusedAdam as the reference
+"""the fused optimiser (mfn_adam_step / mfn_adam_step_dev) against a float64 restatement of apex FusedAdam as the reference
 configures it (train.py:136: FusedAdam(lr, eps=1e-15), betas (0.9, 0.999), bias correction on, no weight decay), with the AMP
 bookkeeping the kernel folds in: gradient unscale, skip on overflow, fp16 shadow refresh, gradient zeroing."""
 import ctypes
@@ -40,8 +39,12 @@ def test_adam_step_matches_fused_adam_restatement():
         p_before = p.clone()
         call("mfn_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(ph), n, 1e-2, 0.9, 0.999, 1e-15, step, scale, ptr(flag), 1, stream_ptr())
         rp, rm, rv = _ref_adam(rp.float(), g0, rm.float(), rv.float(), 1e-2, step, scale)     # from the kernel's own fp32 state of the previous step
-        # m = 0.9 m + 0.1 g cancels when the terms have opposite signs: absolute tolerance = a few fp32 roundings of the terms (|g| * scale <= 0.15)
-        torch.testing.assert_close(m.double(), rm, rtol=1e-6, atol=1e-7)
+        # m = 0.9 m + 0.1 g cancels when the two terms have opposite signs (from step 2 on, ~0.6 % of the entries): the fp32 result then
+        # carries the ABSOLUTE rounding error of the terms (|0.1 g scale| <= 0.015 -> ulp 9e-10, two roundings, FMA contraction either
+        # way) while the sum itself can be 1000x smaller -- round 1's "exp_avg off by 2e-4 relative in 552 / 100 003 entries" under
+        # atol 1e-12.  An fp32 emulation of the kernel's expression on CPU gives max |err| = 1.4e-9 and 550-800 entries beyond rtol 1e-6;
+        # atol 5e-9 is 3.5x that worst case.  Away from cancellation rtol 1e-6 (8 ulp) binds.
+        torch.testing.assert_close(m.double(), rm, rtol=1e-6, atol=5e-9)
         torch.testing.assert_close(v.double(), rv, rtol=2e-6, atol=1e-14)                    # sums of squares: no cancellation
         torch.testing.assert_close(p.double(), rp, rtol=0, atol=2e-7)                        # one fp32 rounding of |p| <= 0.6 plus the update's
         upd, upd_r = (p.double() - p_before.double()), (rp - p_before.double())
