@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-python-layer", action="store_true", help="skip the gpu_reference / frozen_api legs (the reference's python layer on the GPU)")
     return ap.parse_args()
 
 
@@ -118,46 +119,157 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (host cores)
-def cpu_reference(steps, warmup, rays=R_PER_GPU, budget_s=25.0):
-    """the reference training step as a CPU port (oracle/cpu_step.py) on all host cores -> (rays/s, dict)"""
+def cpu_reference(steps, warmup, rays=R_PER_GPU, budget_s=25.0, warm_budget_s=None):
+    """the reference training step as a CPU port (oracle/cpu_step.py) on all host cores -> (rays/s, dict).
+    Same schedule as the GPU arm: steps count from 1 from the procedural Lego occupancy grid, update_density_grid every 16 steps (all
+    cells while step < 256), `warmup` untimed steps first -- so that both arms are timed in the same occupancy regime (round 1 timed
+    the CPU arm on the untouched grid: 25 samples/ray against the GPU arm's 58).  The warm-up is cut at `warm_budget_s` of wall time
+    (reported: warmup_steps_run, same_schedule)."""
     import numpy as np
     from mfnerf_b200 import synthetic as syn
     from oracle.cpu_step import CpuTrainer
+    if warm_budget_s is None:
+        warm_budget_s = float(os.environ.get("MFN_REF_WARM_BUDGET_S", "75"))
+    budget_s = float(os.environ.get("MFN_REF_BUDGET_S", budget_s))
     tr = CpuTrainer(scale=0.5, log2_T=19, threads=os.cpu_count())
     tr.set_density_grid(syn.lego_density_grid(0.5, 1))
     pool = make_pool(2, rays, seed=101)
-    for i in range(max(1, warmup)):
-        tr.train_step(pool[i % 2, 0], pool[i % 2, 1], pool[i % 2, 2])
+    step, t0 = 1, time.perf_counter()
+    for _ in range(max(1, warmup)):
+        tr.training_step(step, pool[step % 2, 0], pool[step % 2, 1], pool[step % 2, 2]); step += 1
+        if time.perf_counter() - t0 > warm_budget_s:
+            break
+    warm_run = step - 1
     t0 = time.perf_counter()
     done = samples = 0
-    for i in range(steps):
-        _, n = tr.train_step(pool[i % 2, 0], pool[i % 2, 1], pool[i % 2, 2])
+    for _ in range(steps):
+        _, n = tr.training_step(step, pool[step % 2, 0], pool[step % 2, 1], pool[step % 2, 2]); step += 1
         done += 1; samples += n
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done * rays / dt, dict(steps_run=done, seconds=dt, samples_per_ray=samples / max(1, done * rays), cores=tr.threads,
-                                  sample=f"{done} full training steps of {rays} rays (AABB, march, field fwd/bwd, composite fw/bw, loss, Adam) "
-                                         f"of the same Lego-shaped workload, {dt:.1f} s of CPU work")
+    return done * rays / dt, dict(steps_run=done, seconds=dt, samples_per_ray=samples / max(1, done * rays), cores=tr.threads, warmup_steps_run=warm_run,
+                                  same_schedule=warm_run >= warmup,
+                                  sample=f"{done} full training steps of {rays} rays (occupancy update every 16 steps, AABB, march, field fwd/bwd, composite fw/bw, "
+                                         f"loss, Adam) of the same Lego-shaped workload after {warm_run} untimed warm-up steps, {dt:.1f} s of CPU work")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 20)
-    v, info = cpu_reference(steps, min(args.warmup, 1))
+    steps = min(args.steps, 24)
+    v, info = cpu_reference(steps, max(1, args.warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps_run"], "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": info["steps_run"], "warmup": info["warmup_steps_run"],
         "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps_run"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_step": R_PER_GPU, "note": "vren/tcnn have no CPU kernels: C restatement of vren + torch "
-                   "transliteration of tcnn (oracle/), all host threads"},
+        "config": {"workload": WORKLOAD, "rays_per_step": R_PER_GPU, "density_grid_update_every": 16, "same_schedule_as_gpu_arm": info["same_schedule"],
+                   "note": "vren/tcnn have no CPU kernels: C restatement of vren + torch transliteration of tcnn (oracle/), all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "samples_per_ray": info["samples_per_ray"],
+        "samples_per_ray": info["samples_per_ray"], "samples_per_sec": v * info["samples_per_ray"],
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ the reference's python layer on the GPU
+def python_layer_arm(kind, dev, pool_dev, steps, warmup):
+    """The reference's UNMODIFIED python layer (models/rendering.py, custom_functions.py, networks.py, losses.py, staged under
+    oracle/_ref/refpy by oracle/build_ref_vren.sh) driving one training_step after the other (train.py:164-190) on the same ray
+    batches as our arm, under autocast + GradScaler (Lightning precision=16) and Adam(eps=1e-15):
+      kind = "gpu_reference": on the reference's OWN vren kernels recompiled for sm_100 (oracle/_ref/vren_ref*.so) + a torch
+             transliteration of the un-vendored tiny-cuda-nn fork (oracle/tcnn_torch.py) -- BASELINE.md's "GPU-ref A+B";
+      kind = "frozen_api"   : on this repo's drop-in modules (vren / tinycudann / torch_scatter over the C ABI) -- what a user
+             gets by running the reference's train.py unchanged.
+    Timed with CUDA events around `steps` steps (host syncs of the reference flow included), outside our arm's timed regions."""
+    import contextlib
+    import glob
+    import importlib.util
+    import types
+    import torch
+    refpy = os.path.join(ROOT, "oracle", "_ref", "refpy")
+    if not os.path.isdir(os.path.join(refpy, "models")):
+        return {"unavailable": "oracle/_ref/refpy not staged (oracle/build_ref_vren.sh runs where /root/reference exists)"}
+    names = ("vren", "tinycudann", "torch_scatter", "losses", "models")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k in names or k.startswith("models.")}
+    try:
+        if kind == "gpu_reference":
+            so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "vren_ref*.so"))
+            if not so:
+                return {"unavailable": "oracle/_ref/vren_ref*.so not built"}
+            spec = importlib.util.spec_from_file_location("vren_ref", so[0])
+            vren_mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(vren_mod)
+            from oracle import tcnn_torch
+            scatter = types.ModuleType("torch_scatter")
+            scatter.segment_csr = lambda src, indptr: torch.segment_reduce(src, "sum", offsets=indptr, axis=0)
+            sys.modules.update(vren=vren_mod, tinycudann=tcnn_torch, torch_scatter=scatter)
+            label = "reference vren kernels recompiled for sm_100 + torch transliteration of tiny-cuda-nn (tcnn itself is not in the tree)"
+        else:
+            import vren as vren_mod  # noqa: F401  (this repo's drop-ins, mf-nerf_b200/ on sys.path)
+            import tinycudann  # noqa: F401
+            import torch_scatter  # noqa: F401
+            label = "reference python layer, unchanged, on this repo's vren / tinycudann / torch_scatter drop-ins"
+        sys.path.insert(0, refpy)
+        try:
+            with contextlib.redirect_stdout(sys.stderr):
+                from models import networks, rendering
+                import losses
+        finally:
+            sys.path.remove(refpy)
+        from mfnerf_b200 import synthetic as syn
+        hp = types.SimpleNamespace(L=16, F=2, T=19, N_min=16, N_max=2048, N_tables=1, grid="Hash", rgb_channels=64, rgb_layers=2)
+        with contextlib.redirect_stdout(sys.stderr):
+            model = networks.NGP(scale=0.5, hparams=hp, rgb_act="Sigmoid").to(dev)
+        G = model.grid_size
+        model.register_buffer("density_grid", torch.from_numpy(syn.lego_density_grid(0.5, 1)).to(dev).reshape(model.cascades, G ** 3).contiguous())   # train.py:78-81
+        ar = torch.arange(G, dtype=torch.int32, device=dev)
+        model.register_buffer("grid_coords", torch.stack(torch.meshgrid(ar, ar, ar, indexing="ij"), -1).reshape(-1, 3).contiguous())
+        vren_mod.packbits(model.density_grid.reshape(-1).contiguous(), 0.5, model.density_bitfield)
+        loss_fn = losses.NeRFLoss(lambda_distortion=0)                                  # opt.py:25 default
+        opt = torch.optim.Adam([p for p in model.parameters() if p.numel() > 0], lr=1e-2, eps=1e-15)   # train.py:136 (apex FusedAdam is not installed)
+        scaler = torch.amp.GradScaler("cuda")
+        state = {"step": 1, "samples": 0}
+
+        def step():
+            s = state["step"]
+            if s % 16 == 0:                                                             # train.py:165-168
+                model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=s < 256, erode=False)
+            b = pool_dev[s % pool_dev.shape[0]]
+            with torch.autocast("cuda", dtype=torch.float16):
+                res = rendering.render(model, b[0], b[1], test_time=False, random_bg=False)
+                ld = loss_fn(res, {"rgb": b[2]})
+                loss = sum(v.mean() for v in ld.values())
+            opt.zero_grad(set_to_none=True)
+            scaler.scale(loss).backward()
+            scaler.step(opt); scaler.update()
+            state["samples"] += int(res["rm_samples"])
+            state["step"] = s + 1
+            return loss
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        state["samples"] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record(); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        R = pool_dev.shape[2]
+        out = {"value": steps * R / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "kind": label,
+               "samples_per_ray": state["samples"] / (steps * R), "samples_per_sec": state["samples"] / (ms * 1e-3), "final_loss": float(loss),
+               "optimizer": "torch.optim.Adam(eps=1e-15) + torch.amp.GradScaler (apex FusedAdam / Lightning are not installed)"}
+        del model, opt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # a baseline leg must never take the main line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    finally:
+        for k in [k for k in list(sys.modules) if k in names or k.startswith("models.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -367,10 +479,19 @@ def run_ours(args):
                   "field_rows_per_ray": rows / (800 * 800), "tiles": f"{world} row tile(s), no collective",
                   "schedule": f"N_samples = clamp(N_rays / N_alive, {RENDER_MIN_CHUNK}, 64) per iteration (reference: lower bound 1; same image, fewer iterations)"}
 
+    # ---- the reference's python layer on the same GPU, same batches (rank 0 of a 1-GPU run only): GPU-ref A+B and the frozen API
+    gpu_ref = frozen = None
+    if rank == 0 and world == 1 and not args.no_python_layer:
+        eng.flush(); torch.cuda.synchronize(dev)
+        n_ref, w_ref = min(K, 64), min(W, 64)
+        gpu_ref = python_layer_arm("gpu_reference", dev, pool_dev, n_ref, w_ref)
+        frozen = python_layer_arm("frozen_api", dev, pool_dev, n_ref, w_ref)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, info = cpu_reference(12, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
+        v, info = cpu_reference(12, W)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"], "samples_per_ray": info["samples_per_ray"],
+               "same_schedule_as_gpu_arm": info["same_schedule"]}
 
     if rank == 0:
         line = {
@@ -385,7 +506,7 @@ def run_ours(args):
             "samples_per_sec": samples_dev / (ms_dev * 1e-3), "samples_per_ray": samples_dev / rays_total,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(3 * R * 3 * 4), "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K,
                     "api": "NGPEngine.train_step_packed(host_pinned_batch) -> C ABI; loss copied to pinned host memory every step"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "render": render,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "frozen_api": frozen, "render": render,
             "final_loss_terms": final_loss,
         }
         print(json.dumps(line), flush=True)

@@ -17,17 +17,18 @@ static bool use_fused(const mfn_field_cfg* c) {
     return !v1 && fused_field_supported(c);
 }
 
-// workspace of the fused path: [tile blobs | rgb copy (n,3) f32 | dfeats (n,32) f16 | weight-gradient partials]
-struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, count, total; };
+// workspace of the fused path: [saved X tiles | rgb outputs (n,4) f16 | dfeats (n,32) f16 | weight-gradient partials | x01 (n,4) f32 | dirs (n,3) f32 | count]
+struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, dirs, count, total; };
 static FusedWs fused_ws(int64_t n, bool training) {
     FusedWs w{};
     size_t o = 0;
     if (training) {
         w.blobs = o; o += fused_blob_bytes(n);
-        w.rgb = o; o += (size_t)(n * 12 + 255) / 256 * 256;
+        w.rgb = o; o += (size_t)(n * 8 + 255) / 256 * 256;
         w.dfeats = o; o += (size_t)((n + 63) / 64 * 64) * 64;
         w.partials = o; o += (fused_partial_bytes() + 255) / 256 * 256;
         w.x01 = o; o += (size_t)(n * 16 + 255) / 256 * 256;
+        w.dirs = o; o += (size_t)(n * 12 + 255) / 256 * 256;
         w.count = o; o += 256;         // int32: the sample count of the forward pass (mfn_field_count_ptr)
     }
     w.total = o > 256 ? o : 256;
@@ -197,7 +198,7 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         const bool train = (size_t)workspace_bytes >= fw.total;
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
         f.sigmas = sigmas; f.rgbs = rgbs;
-        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.x01 = (float4*)(ws + fw.x01); f.n_out = (int32_t*)(ws + fw.count); }
+        if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.x01 = (float4*)(ws + fw.x01); f.n_out = (int32_t*)(ws + fw.count); }
         { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
     }
@@ -236,7 +237,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         const FusedWs fw = fused_ws(n_max, true);
         if ((size_t)workspace_bytes < fw.total) { set_error("mfn_field_bwd: workspace too small"); return MFN_ERR_ARG; }
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, nullptr, n_max, n_dev);
-        f.blobs = (unsigned char*)ws + fw.blobs; f.rgbs_copy = (float*)(ws + fw.rgb); f.dfeats = (__half*)(ws + fw.dfeats);
+        f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.dfeats = (__half*)(ws + fw.dfeats);
         f.dfeats_stride = (n_max + 63) / 64 * 64;
         f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
         WgradReduce wr{};

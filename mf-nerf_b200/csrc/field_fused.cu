@@ -10,11 +10,15 @@
 //   CAT tile = [SH4(dir) | h] -> mma CAT.W3^T -> ReLU -> mma .W4^T -> ReLU -> mma .W5^T -> sigmoid -> rgb.
 //   X, H and CAT live one after the other in ONE 16 KiB region and the two accumulators share 64 TMEM columns (36 KiB of shared
 //   memory and 48 registers per thread are what lets 5 CTAs share an SM; the gather is bound by resident parallelism).
-//   Nothing but xyz/dir in and sigma/rgb out touches HBM at inference.  In training the five activation tiles are also stored,
-//   as one contiguous 64 KiB blob per tile *in the shared-memory layout*, each with one bulk async store (shared -> global, waited
-//   for before the region is overwritten), so that the backward kernel fetches a tile with a single bulk async copy
-//   (cp.async.bulk, the 1-D TMA path) and feeds it to the tensor cores without any re-staging.
+//   Nothing but xyz/dir in and sigma/rgb out touches HBM at inference.  In training the forward pass saves, per sample, only what
+//   the backward pass cannot cheaply recompute: the encoded features X (64 B, the 8 KiB X tile *in the shared-memory layout*, one
+//   bulk async store per tile), the view direction (12 B), the fp16 rgb outputs (8 B) and the normalised position for the scatter
+//   kernel (16 B) -- 100 B/sample instead of round 1's 540 B/sample of activation blobs.  The hidden activations H1 / CAT / H2 /
+//   H3 never leave the SM: the backward kernel re-runs the four forward MMAs on the saved X tile (same instruction shapes, same
+//   operands -> bit-identical activations; the tensor pipe was 4-17 % busy) before its dgrad / wgrad chain.
+//   (MFN_FIELD_SAVE=full keeps round 1's behaviour -- all five tiles stored, 64 KiB per tile -- for A/B measurements.)
 // Backward, one CTA = 128 samples, 256 threads, persistent, 2 CTAs / SM (88 KiB of shared memory, 256 TMEM columns):
+//   one 8 KiB bulk async copy (X tile) -> recompute H1, h, CAT = [SH(dir) | h], H2, H3 ->
 //   dZ5 = dL/drgb * sigmoid' -> [dgrad mma -> TMEM -> ReLU mask -> dZ tile (in place of the activation it masks)] x 4 -> dX;
 //   the weight gradients dW = dZ^T.A are tcgen05 MMAs with M = 64, both operands read MN-major from the very same tiles, and
 //   they ACCUMULATE IN TMEM across all tiles of the CTA (fp32); one partial per CTA is written at the end and an extra grid row of
@@ -51,7 +55,8 @@ constexpr int kFwdX = kWEnd, kFwdH = kFwdX + kFT * 32 * 2, kFwdC = kFwdH + kFT *
 constexpr int kBwdBlob = kWEnd, kBwdDZo = kBwdBlob + kBlob, kBwdSmem = kBwdDZo + kFT * 16 * 2;
 // TMEM columns
 constexpr int kFwdCols = 128, kAccH = 0, kAccO = 64;
-constexpr int kBwdCols = 256, kAccW5 = 64, kAccW4 = 80, kAccW3 = 144, kAccW2 = 176, kAccW1 = 192;
+constexpr int kBwdCols = 256, kAccW5 = 64, kAccW4 = 80, kAccW3 = 144, kAccW2 = 176, kAccW1 = 192, kAccO2 = 224;   // kAccO2: h of the recomputed forward
+constexpr int kBlobX = kFT * 32 * 2;     // saved per tile when the backward pass recomputes the hidden activations: the X tile only
 constexpr int kNumWg = 64 * 32 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;   // 10240 weight-gradient floats per partial
 
 // global row-major [rows][cols] fp16 matrix -> row-core tile in shared memory
@@ -162,6 +167,16 @@ __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict
     return pack2(f0, f1);
 }
 
+// SH (degree 4) of the normalised direction mapped like networks.py:145-146 -> 16 fp16 values = CAT[:, 0:16] of one row
+__device__ __forceinline__ void sh_of_dir(float dx, float dy, float dz, uint4& o0, uint4& o1) {
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float ux = (dx / nrm + 1.0f) / 2.0f, uy = (dy / nrm + 1.0f) / 2.0f, uz = (dz / nrm + 1.0f) / 2.0f;
+    float s[16];
+    sh4_eval(fmaf(ux, 2.f, -1.f), fmaf(uy, 2.f, -1.f), fmaf(uz, 2.f, -1.f), s);
+    o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
+    o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
+}
+
 __device__ __forceinline__ float act_out(float x, int act) {
     if (act == MFN_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-x));
     if (act == MFN_ACT_EXP) return __expf(x);
@@ -189,8 +204,9 @@ __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* t
 }
 
 // ------------------------------------------------------------------------------------------------------------------ forward
-// MODE 0: inference (sigma + rgb), 1: training (also writes the activation blobs), 2: density only (sigma),
-// 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107).
+// MODE 0: inference (sigma + rgb), 1: training (also saves X tile, direction, fp16 rgb and normalised position), 2: density only (sigma),
+// 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107),
+// 4: training with all five activation tiles stored (round 1's 64 KiB blobs; MFN_FIELD_SAVE=full).
 // 256 threads: thread t works on sample row t % 128 (= its TMEM lane); the two threads of a row split the 16 grid levels in the
 // gather phase and the 64 accumulator columns in the hidden-layer epilogues.  In training mode every published tile is also sent
 // to the blob with one bulk async store (shared -> global) issued by thread 0.
@@ -200,12 +216,13 @@ constexpr bool kTrainAlias = true;      // training mode too: one tile region, e
 #define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
 
 template <int NH2, int MODE>
-__global__ void __launch_bounds__(kFwdThreads, (MODE == 1 && !kTrainAlias) ? 4 : 5)
+__global__ void __launch_bounds__(kFwdThreads, ((MODE == 1 || MODE == 4) && !kTrainAlias) ? 4 : 5)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
+    constexpr bool TRAIN = (MODE == 1 || MODE == 4), FULL = (MODE == 4), RGB = (MODE < 2 || MODE == 4);
     // Inference / density modes keep no tile alive across stages, so X, H and CAT share ONE 16 KiB region and the 16-column output
     // accumulator shares the hidden accumulator's TMEM columns: 36 KiB + 64 columns per CTA -> 5 CTAs / SM instead of 4 (the gather
     // is bound by resident parallelism).  Training mode streams every tile to the blob and keeps the three regions apart.
-    constexpr bool ALIAS = (MODE != 1) || kTrainAlias;
+    constexpr bool ALIAS = !TRAIN || kTrainAlias;
     constexpr int oX = kFwdX, oH = ALIAS ? kFwdX : kFwdH, oC = ALIAS ? kFwdX : kFwdC;
     constexpr int accO = ALIAS ? kAccH : kAccO;
     constexpr int nCols = ALIAS ? 64 : kFwdCols;
@@ -216,9 +233,9 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const int row = tid & (kFT - 1), hsel = tid >> 7;
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
-    if (MODE == 1 && a.n_out && blockIdx.x == 0 && tid == 0) *a.n_out = (int32_t)n;     // the backward pass's own copy of the count
+    if (TRAIN && a.n_out && blockIdx.x == 0 && tid == 0) *a.n_out = (int32_t)n;     // the backward pass's own copy of the count
     if ((int64_t)blockIdx.x >= n_tiles) return;      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
-    stage_all_weights<NH2>(smem, a, tid, kFwdThreads, MODE < 2);
+    stage_all_weights<NH2>(smem, a, tid, kFwdThreads, RGB);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, nCols);
     fence_async_smem();
@@ -236,7 +253,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
-        unsigned char* blob = (MODE == 1) ? a.blobs + (size_t)tile * kBlob : nullptr;
+        unsigned char* blob = TRAIN ? a.blobs + (size_t)tile * (FULL ? kBlob : kBlobX) : nullptr;
         MFN_TS(0);
         // ---- hash-grid gather -> X tile: lane pair (2p, 2p+1) of warp w works on row 16w + p, all 16 levels
         {
@@ -249,7 +266,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
                 y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
                 z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
-                if (MODE == 1 && xb == 1) a.x01[gi] = make_float4(x, y, z, 0.f);
+                if (TRAIN && xb == 1) a.x01[gi] = make_float4(x, y, z, 0.f);
             }
 #pragma unroll 2
             for (int l = 0; l < 16; ++l) {
@@ -268,7 +285,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBX, smem + oX, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: H1 overwrites X)
+            if (TRAIN) { bulk_s2g_hint(blob + kBX, smem + oX, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: H1 overwrites X)
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -286,7 +303,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + accO, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + kBH1, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: CAT overwrites H1)
+            if (FULL) { bulk_s2g_hint(blob + kBH1, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }   // (shared region: CAT overwrites H1)
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -303,23 +320,19 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             if (MODE == 3) {
                 if (valid) { uint4* ho = reinterpret_cast<uint4*>(a.h_out + 16 * i); ho[0] = o0; ho[1] = o1; }
             } else if (valid) a.sigmas[i] = expf(__low2float(*reinterpret_cast<const __half2*>(&o0.x)));
-            if (MODE < 2) {
+            if (RGB) {
                 *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 16, 32)) = o0;
                 *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 24, 32)) = o1;
             }
-        } else if (MODE < 2) {
+        } else if (RGB) {
             // the partner thread of the row meanwhile encodes the direction: SH of the normalised direction -> CAT[:, 0:16]
             // (networks.py:145-146); CAT may overlay H1, which the layer-2 MMA has finished reading
             mbar_wait(&bar, phase);
             uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
             if (valid) {
                 const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
-                const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-                const float ux = (dx / nrm + 1.0f) / 2.0f, uy = (dy / nrm + 1.0f) / 2.0f, uz = (dz / nrm + 1.0f) / 2.0f;
-                float s[16];
-                sh4_eval(fmaf(ux, 2.f, -1.f), fmaf(uy, 2.f, -1.f), fmaf(uz, 2.f, -1.f), s);
-                o0.x = pack2(s[0], s[1]); o0.y = pack2(s[2], s[3]); o0.z = pack2(s[4], s[5]); o0.w = pack2(s[6], s[7]);
-                o1.x = pack2(s[8], s[9]); o1.y = pack2(s[10], s[11]); o1.z = pack2(s[12], s[13]); o1.w = pack2(s[14], s[15]);
+                if (MODE == 1) { a.dirs_copy[3 * i] = dx; a.dirs_copy[3 * i + 1] = dy; a.dirs_copy[3 * i + 2] = dz; }   // the backward pass re-encodes it
+                sh_of_dir(dx, dy, dz, o0, o1);
             }
             *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 0, 32)) = o0;
             *reinterpret_cast<uint4*>(smem + oC + tile_off(row, 8, 32)) = o1;
@@ -330,14 +343,14 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         tc_fence_before();
         __syncthreads();
         MFN_TS(7);
-        if (MODE >= 2) continue;   // (uniform) density only / raw outputs
+        if (!RGB) continue;   // (uniform) density only / raw outputs
         // ---- rgb layer 1: H2 = relu(CAT . W3^T)
         if (tid == 0) {
             tc_fence_after();
             const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + oC, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }
+            if (FULL) { bulk_wait_read0(); bulk_s2g_hint(blob + kBC, smem + oC, kFT * 32 * 2, pol_stream); bulk_commit(); if (ALIAS) bulk_wait_read0(); }
             mma_commit(&bar);
         }
         mbar_wait(&bar, phase); phase ^= 1u;
@@ -353,7 +366,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 const uint32_t id = idesc_f16(128, 64, false, false);
 #pragma unroll
                 for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
-                if (MODE == 1) { bulk_s2g_hint(blob + kBH2, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
+                if (FULL) { bulk_s2g_hint(blob + kBH2, smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); bulk_wait_read0(); }
                 mma_commit(&bar);
             }
             mbar_wait(&bar, phase); phase ^= 1u;
@@ -369,7 +382,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             const uint32_t id = idesc_f16(128, 16, false, false);
 #pragma unroll
             for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + accO, desc_kmajor(sbase + oH, 64, k0), desc_kmajor(sbase + kW5, 64, k0), id, k0 > 0);
-            if (MODE == 1) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); }
+            if (FULL) { bulk_s2g_hint(blob + (NH2 == 2 ? kBH3 : kBH2), smem + oH, kFT * 64 * 2, pol_stream); bulk_commit(); }
             mma_commit(&bar);
         }
         if (hsel == 0) {
@@ -379,21 +392,23 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             tmem_ld_x8(trow + accO, r);
             tmem_ld_wait();
             if (valid) {
+                __half hv[4];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float v = __half2float(__float2half_rn(act_out(__uint_as_float(r[k]), a.rgb_act)));
-                    a.rgbs[3 * i + k] = v;
-                    if (MODE == 1) a.rgbs_copy[3 * i + k] = v;
+                    hv[k] = __float2half_rn(act_out(__uint_as_float(r[k]), a.rgb_act));
+                    a.rgbs[3 * i + k] = __half2float(hv[k]);
                 }
+                hv[3] = __float2half_rn(0.f);
+                if (TRAIN) a.rgb_h[i] = *reinterpret_cast<const uint2*>(hv);      // the outputs ARE fp16 values: 8 B/sample for the backward pass
             }
         }
         phase ^= 1u;
-        if (MODE == 1 && tid == 0) bulk_wait_read0();   // the last stores (CAT, last hidden tile) have read shared memory: the next tile may overwrite it
+        if (FULL && tid == 0) bulk_wait_read0();   // the last stores (CAT, last hidden tile) have read shared memory: the next tile may overwrite it
         tc_fence_before();
         __syncthreads();   // TMEM and the tiles are free for the next tile
         MFN_TS(8);
     }
-    if (MODE == 1 && tid == 0) bulk_wait0();
+    if (TRAIN && tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, nCols);
@@ -425,7 +440,9 @@ __device__ __forceinline__ void mask_epilogue32(uint32_t taddr, unsigned char* t
     }
 }
 
-template <int NH2>
+// RC = true: only the X tile was saved; H1, h, CAT, H2, H3 are recomputed here (four more MMAs + epilogues per tile, nothing read
+// from HBM but 64 + 12 + 8 B/sample).  RC = false: round 1's path, the five tiles come back as one 64 KiB bulk copy.
+template <int NH2, bool RC>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -457,17 +474,21 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
-        if (tid == 0) {   // the whole activation blob of this tile with one bulk async copy
-            mbar_arrive_expect_tx(&bar_load, NH2 == 2 ? kBlob : kBH3);
-            bulk_g2s_hint(sBlob, a.blobs + (size_t)tile * kBlob, NH2 == 2 ? kBlob : kBH3, &bar_load, policy_evict_first());
+        if (tid == 0) {   // RC: the saved X tile; else the whole activation blob of this tile -- one bulk async copy either way
+            constexpr uint32_t bytes = RC ? kBlobX : (NH2 == 2 ? kBlob : kBH3);
+            mbar_arrive_expect_tx(&bar_load, bytes);
+            bulk_g2s_hint(sBlob, a.blobs + (size_t)tile * (RC ? kBlobX : kBlob), bytes, &bar_load, policy_evict_first());
         }
         // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
         if (hsel == 0) {
             float g[3] = {0.f, 0.f, 0.f};
             if (valid) {
+                const uint2 yh = a.rgb_h[i];
+                const float2 y01 = __half22float2(*reinterpret_cast<const __half2*>(&yh.x));
+                const float y3[3] = {y01.x, y01.y, __low2float(*reinterpret_cast<const __half2*>(&yh.y))};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float yv = a.rgbs_copy[3 * i + k];
+                    const float yv = y3[k];
                     float d = a.dL_drgbs[3 * i + k] * a.loss_scale;
                     if (a.rgb_act == MFN_ACT_SIGMOID) d *= yv * (1.f - yv);
                     else if (a.rgb_act == MFN_ACT_EXP) d *= yv;
@@ -479,11 +500,84 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             bad |= !isfinite(__low2float(hh[0])) || !isfinite(__high2float(hh[0])) || !isfinite(__low2float(hh[1]));
             *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 0, 16)) = o0;
             *reinterpret_cast<uint4*>(smem + kBwdDZo + tile_off(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
+        } else if (RC) {   // the partner thread re-encodes the view direction: CAT[:, 0:16] (same code, same bits as the forward pass)
+            uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
+            if (valid) sh_of_dir(a.dirs_copy[3 * i], a.dirs_copy[3 * i + 1], a.dirs_copy[3 * i + 2], o0, o1);
+            *reinterpret_cast<uint4*>(sBlob + kBC + tile_off(row, 0, 32)) = o0;
+            *reinterpret_cast<uint4*>(sBlob + kBC + tile_off(row, 8, 32)) = o1;
         }
         mbar_wait(&bar_load, ph_load); ph_load ^= 1u;
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (RC) {
+            // ---- recomputed forward: H1 = relu(X.W1^T) ; h = H1.W2^T -> CAT[:, 16:32] ; H2 = relu(CAT.W3^T) ; H3 = relu(H2.W4^T)
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+                for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
+                mma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            tc_fence_after();
+            relu_epilogue32(trow + kAccH, sBlob + kBH1, row, 32 * hsel);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_f16(128, 16, false, false);
+#pragma unroll
+                for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO2, desc_kmajor(sH1, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
+                mma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            tc_fence_after();
+            if (hsel == 0) {
+                uint32_t r[16];
+                tmem_ld_x16(trow + kAccO2, r);
+                tmem_ld_wait();
+                uint4 o0, o1;
+                o0.x = pack2(__uint_as_float(r[0]), __uint_as_float(r[1])); o0.y = pack2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+                o0.z = pack2(__uint_as_float(r[4]), __uint_as_float(r[5])); o0.w = pack2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+                o1.x = pack2(__uint_as_float(r[8]), __uint_as_float(r[9])); o1.y = pack2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+                o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+                *reinterpret_cast<uint4*>(sBlob + kBC + tile_off(row, 16, 32)) = o0;
+                *reinterpret_cast<uint4*>(sBlob + kBC + tile_off(row, 24, 32)) = o1;
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+                for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
+                mma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            tc_fence_after();
+            relu_epilogue32(trow + kAccH, sBlob + kBH2, row, 32 * hsel);
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (NH2 == 2) {
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t id = idesc_f16(128, 64, false, false);
+#pragma unroll
+                    for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sH2, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
+                    mma_commit(&bar_mma);
+                }
+                mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+                tc_fence_after();
+                relu_epilogue32(trow + kAccH, sBlob + kBH3, row, 32 * hsel);
+                fence_async_smem();
+                tc_fence_before();
+                __syncthreads();
+            }
+        }
         // ---- stage A: dH_last = dZ5 . W5 ;  dW5^T += H_last^T . dZ5
         if (tid == 0) {
             tc_fence_after();
@@ -655,13 +749,19 @@ bool fused_field_supported(const mfn_field_cfg* c) {
            (c->rgb_hidden == 1 || c->rgb_hidden == 2);
 }
 int fused_bwd_max_ctas() { return 2 * num_sms(); }
-size_t fused_blob_bytes(int64_t n_max) { return (size_t)ceil_div(n_max, kFT) * kBlob; }
+// MFN_FIELD_SAVE=full: round 1's behaviour (all five activation tiles stored, 64 KiB per tile) for A/B measurements
+bool fused_save_full() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MFN_FIELD_SAVE"); v = (e && e[0] == 'f') ? 1 : 0; }
+    return v == 1;
+}
+size_t fused_blob_bytes(int64_t n_max) { return (size_t)ceil_div(n_max, kFT) * (fused_save_full() ? kBlob : kBlobX); }
 size_t fused_partial_bytes() { return (size_t)fused_bwd_max_ctas() * kNumWg * sizeof(float); }
 
 template <int NH2, int MODE>
 static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
-    constexpr int smem_bytes = (MODE == 1 && !kTrainAlias) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // one shared tile region
-    constexpr int max_ctas = (MODE == 1 && !kTrainAlias) ? 4 : 5;
+    constexpr int smem_bytes = ((MODE == 1 || MODE == 4) && !kTrainAlias) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // one shared tile region
+    constexpr int max_ctas = ((MODE == 1 || MODE == 4) && !kTrainAlias) ? 4 : 5;
     static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
@@ -675,19 +775,23 @@ static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
 int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st) {
     ProfScope ps(mode >= 2 ? "density_fwd" : "field_fwd", st);
     if (mode == 3) { launch_fwd<1, 3>(a, m, st); return check_launch("mfn_geo_fwd(fused)", st); }
-    if (rgb_hidden == 2) { if (mode == 0) launch_fwd<2, 0>(a, m, st); else if (mode == 1) launch_fwd<2, 1>(a, m, st); else launch_fwd<2, 2>(a, m, st); }
-    else { if (mode == 0) launch_fwd<1, 0>(a, m, st); else if (mode == 1) launch_fwd<1, 1>(a, m, st); else launch_fwd<1, 2>(a, m, st); }
+    if (mode == 1 && fused_save_full()) mode = 4;
+    if (rgb_hidden == 2) {
+        if (mode == 0) launch_fwd<2, 0>(a, m, st); else if (mode == 1) launch_fwd<2, 1>(a, m, st); else if (mode == 4) launch_fwd<2, 4>(a, m, st); else launch_fwd<2, 2>(a, m, st);
+    } else {
+        if (mode == 0) launch_fwd<1, 0>(a, m, st); else if (mode == 1) launch_fwd<1, 1>(a, m, st); else if (mode == 4) launch_fwd<1, 4>(a, m, st); else launch_fwd<1, 2>(a, m, st);
+    }
     return check_launch("mfn_field_fwd(fused)", st);
 }
 
-template <int NH2>
+template <int NH2, bool RC>
 static int launch_bwd(const FusedArgs& a, cudaStream_t st) {
-    static bool once = (cudaFuncSetAttribute(field_bwd_fused_kernel<NH2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), true);
+    static bool once = (cudaFuncSetAttribute(field_bwd_fused_kernel<NH2, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
     const int64_t cap = fused_bwd_max_ctas();
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
-    field_bwd_fused_kernel<NH2><<<grid, kBwdThreads, kBwdSmem, st>>>(a);
+    field_bwd_fused_kernel<NH2, RC><<<grid, kBwdThreads, kBwdSmem, st>>>(a);
     return (int)grid;
 }
 
@@ -695,7 +799,8 @@ int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_para
     int grid;
     {
         ProfScope ps("field_bwd", st);
-        grid = rgb_hidden == 2 ? launch_bwd<2>(a, st) : launch_bwd<1>(a, st);
+        if (fused_save_full()) grid = rgb_hidden == 2 ? launch_bwd<2, false>(a, st) : launch_bwd<1, false>(a, st);
+        else grid = rgb_hidden == 2 ? launch_bwd<2, true>(a, st) : launch_bwd<1, true>(a, st);
     }
     wr->partials = a.partials; wr->n_parts = grid; wr->stride = kNumWg;
     wr->n_sigma = 3072; wr->n_rgb = 64 * 32 + (rgb_hidden - 1) * 64 * 64 + 16 * 64;

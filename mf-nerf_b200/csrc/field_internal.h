@@ -71,10 +71,12 @@ struct FusedArgs {
     const __half* w_sigma;   // [W1 64x32][W2 16x64]
     const __half* w_rgb;     // [W3 64x32]([W4 64x64])[W5 16x64]
     float* sigmas; float* rgbs;
-    float* rgbs_copy;        // training: second copy of rgbs kept in the workspace for the backward pass
+    uint2* rgb_h;            // training: the rgb outputs as 3 fp16 (+ pad) per sample, kept in the workspace for the backward pass
+    float* dirs_copy;        // training: (n,3) view directions, kept in the workspace (the backward pass re-encodes them; the caller's
+                             // array may already hold the next step's samples)
     __half* h_out;           // mode 3: (n, 16) fp16 raw outputs of the sigma network
     int32_t* n_out;          // training: where the forward pass leaves min(*n_dev, n_max) for the backward pass (workspace)
-    unsigned char* blobs;    // training: activation tiles, 64 KiB per 128 samples
+    unsigned char* blobs;    // training: the saved X tile, 8 KiB per 128 samples (MFN_FIELD_SAVE=full: all five tiles, 64 KiB)
     int rgb_act;
     // backward only
     const float* dL_dsigmas; const float* dL_drgbs; float loss_scale;

@@ -38,14 +38,14 @@ class _ParamCache:
     """fp16 shadow of the fp32 master parameters, re-cast on EVERY forward (one cast kernel, ~11 us for the 11.4 M parameters of
     the Lego configuration).  It must not be keyed on `Parameter._version`: the reference trainer's optimiser is apex FusedAdam
     (train.py:23,136), which updates `p.data` through raw pointers and never bumps the version counter -- a version-keyed cache
-    would keep serving the initial weights while the fp32 masters drift.  Grad-enabled forwards get a fresh tensor (autograd saves
-    it for backward); no-grad forwards (NGP.density in update_density_grid, the test-time render loop) reuse one buffer."""
+    would keep serving the initial weights while the fp32 masters drift.  The autograd Functions get a fresh tensor (they save it
+    for backward); the no-grad fast path (NGP.density in update_density_grid, the test-time render loop) reuses one buffer."""
 
     def __init__(self):
         self._buf = None
 
-    def get(self, p):
-        if torch.is_grad_enabled() and p.requires_grad:
+    def get(self, p, fresh=True):
+        if fresh:
             return p.detach().to(torch.float16)
         if self._buf is None or self._buf.shape != p.shape or self._buf.device != p.device:
             self._buf = torch.empty_like(p, dtype=torch.float16)
@@ -248,6 +248,6 @@ class NetworkWithInputEncoding(nn.Module):
             if self._geo_fused is None:
                 self._geo_fused = F.geo_fused(self._geo_cfg) and self.out_act in ("None", "none", None)
             if self._geo_fused and x.is_cuda:
-                out = F.geo_fwd(x.detach().float().contiguous(), self._cache.get(self.params), self._geo_cfg)
+                out = F.geo_fwd(x.detach().float().contiguous(), self._cache.get(self.params, fresh=False), self._geo_cfg)
                 return out[:, :self.n_output_dims]
         return _EncMlpFn.apply(x, self.params, self)

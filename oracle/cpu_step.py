@@ -38,7 +38,45 @@ class CpuTrainer:
         self.rng = np.random.RandomState(seed)
 
     def set_density_grid(self, grid, thr=0.5):
-        orc.packbits(np.ascontiguousarray(grid, np.float32).reshape(-1), thr, self.bitfield)
+        self.density_grid = np.ascontiguousarray(grid, np.float32).reshape(self.cascades, G ** 3).copy()
+        orc.packbits(self.density_grid.reshape(-1), thr, self.bitfield)
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95, chunk=1 << 19):
+        """networks.py:242-271 (+ get_all_cells :157-168, sample_uniform_and_occupied_cells :170-197) on the host"""
+        G3 = G ** 3
+        tmp = np.zeros_like(self.density_grid)
+        for c in range(self.cascades):
+            if warmup:
+                indices = np.arange(G3, dtype=np.int64)
+                coords = orc.morton3D_invert(indices.astype(np.int32))
+            else:
+                M = G3 // 4
+                coords1 = self.rng.randint(0, G, size=(M, 3)).astype(np.int32)
+                indices1 = orc.morton3D(coords1).astype(np.int64)
+                occ = np.nonzero(self.density_grid[c] > density_threshold)[0]
+                indices2 = occ[self.rng.randint(0, len(occ), size=M)] if len(occ) > 0 else occ
+                coords2 = orc.morton3D_invert(indices2.astype(np.int32))
+                indices, coords = np.concatenate([indices1, indices2]), np.concatenate([coords1, coords2])
+            sc = min(2.0 ** (c - 1), self.scale)
+            hgs = sc / G
+            xyz = (coords.astype(np.float32) / (G - 1) * 2 - 1) * (sc - hgs)
+            xyz += (self.rng.rand(*xyz.shape).astype(np.float32) * 2 - 1) * hgs
+            sig = np.empty(xyz.shape[0], np.float32)
+            for i in range(0, xyz.shape[0], chunk):
+                sig[i:i + chunk] = self.model.density_h(torch.from_numpy(xyz[i:i + chunk]))[0].numpy()
+            tmp[c, indices] = sig
+        g = self.density_grid
+        self.density_grid = np.where(g < 0, g, np.maximum(g * decay, tmp)).astype(np.float32)
+        pos = self.density_grid[self.density_grid > 0]
+        mean = float(pos.mean()) if pos.size else 0.0
+        orc.packbits(self.density_grid.reshape(-1), min(mean, density_threshold), self.bitfield)
+
+    def training_step(self, global_step, rays_o, rays_d, target):
+        """train.py:164-190: occupancy update every 16 steps (all cells during the first 256), then the optimisation step"""
+        if global_step % 16 == 0:
+            self.update_density_grid(warmup=global_step < 256)
+        return self.train_step(rays_o, rays_d, target)
 
     def train_step(self, rays_o, rays_d, target, lambda_opacity=1e-3):
         """one optimisation step on (R,3) float32 numpy rays -> (loss, n_samples)"""

@@ -206,11 +206,17 @@ def test_device_side_render_equals_per_op_loop():
 
 
 def test_pipelined_and_data_parallel_step_paths_reproduce_the_plain_path():
-    """three ways to run the same 12 training steps on the same batches with the same jitter:
-      plain      : everything on one stream, optimiser inside the step (pipelined=False)
-      pipelined  : train_step_packed -- three-stream pipeline, marching front of step t+1 overlapping backward / scatter / Adam of step t
-      data-par.  : the world_size > 1 code path (reduce-scatter + sharded Adam + all-gather of the fp16 shadow) on a 1-rank NCCL group
-    The kernels and their order per datum are the same, so the parameters must agree up to the float-atomic summation order."""
+    """four runs of the same 12 training steps on the same batches with the same jitter:
+      plain (twice): everything on one stream, optimiser inside the step (pipelined=False) -- the second run measures the noise floor
+      pipelined    : train_step_packed -- three-stream pipeline, marching front of step t+1 overlapping backward / scatter / Adam of step t
+      data-par.    : the world_size > 1 code path (reduce-scatter + sharded Adam + all-gather of the fp16 shadow) on a 1-rank NCCL group
+    The kernels and their order per datum are the same; what differs between ANY two runs (also two plain ones) is the order of the fp32
+    atomic adds of the hash-grid scatter.  Adam with eps = 1e-15 turns that last-bit noise into a +-lr step wherever a gradient sum
+    cancels to ~0 (first update of an entry: m/sqrt(v) = sign(g)): round 1's failure was exactly that -- 3 of 935 600 entries (level 5),
+    |d| = 2.4e-3 against a 7.6e-4 bound, between two runs of the SAME plain path, reproduced 4/4 on a fresh B200 (tools/repro_threeway.py).
+    So the comparison is: the loss trajectory of every step (a stream race on the sample arrays, the workspace or the parameters would
+    move it by orders of magnitude more than 1e-4), the marched sample count, and the parameters entry by entry with a bounded number of
+    sign-flip outliers, each bounded by what Adam can move an entry in 12 steps."""
     import torch.distributed as dist
     if not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=torch.device("cuda", 0))
@@ -220,25 +226,33 @@ def test_pipelined_and_data_parallel_step_paths_reproduce_the_plain_path():
         tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).float()
         batches.append(torch.stack([torch.from_numpy(rays["rays_o"]), torch.from_numpy(rays["rays_d"]), tgt]).cuda().contiguous())
     noise = torch.rand(256, device="cuda", generator=torch.Generator("cuda").manual_seed(6))
+    LR, STEPS = 1e-2, 12
     outs = []
-    for kw in (dict(pipelined=False), dict(pipelined=True), dict(force_dp_path=True)):
-        eng = _engine(256, **kw)
+    for kw in (dict(pipelined=False), dict(pipelined=False), dict(pipelined=True), dict(force_dp_path=True)):
+        eng = _engine(256, lr=LR, **kw)
         eng.fixed_noise = noise
+        losses = torch.zeros(STEPS + 1, 3).pin_memory()
         for s in range(1, 4):
             eng.train_step_packed(batches[s % 3], global_step=s)
+            eng.loss_to_host(losses[s])
         eng.capture()
-        for s in range(4, 13):
+        for s in range(4, STEPS + 1):
             eng.train_step_packed(batches[s % 3], global_step=s)          # no flush between steps: the optimiser stays in flight
+            eng.loss_to_host(losses[s])
         p = eng.gather_master_params().clone()
         torch.cuda.synchronize()
-        outs.append((p, eng.params_h.float().clone(), eng.loss_terms.clone(), int(eng.counter[0])))
+        outs.append((p, eng.params_h.float().clone(), losses[1:].clone(), int(eng.counter[0])))
     dist.destroy_process_group()
     scale = outs[0][0].abs().max()
-    for other in outs[1:]:
-        assert other[3] == outs[0][3]                                           # same samples marched in the last step
-        assert (outs[0][0] - other[0]).abs().max() <= 2e-3 * scale
-        assert (outs[0][1] - other[1]).abs().max() <= 2e-3 * scale
-        torch.testing.assert_close(outs[0][2], other[2], rtol=1e-2, atol=1e-5)
+    n = outs[0][0].numel()
+    for k, other in enumerate(outs[1:]):
+        assert other[3] == outs[0][3], k                                        # same samples marched in the last step
+        torch.testing.assert_close(other[2], outs[0][2], rtol=1e-4, atol=1e-7)  # every step's loss terms (observed: 3e-7 relative)
+        for j in (0, 1):                                                        # fp32 masters, fp16 shadow
+            d = (outs[0][j] - other[j]).abs()
+            outliers = int((d > 2e-3 * scale).sum())
+            assert outliers <= max(8, n // 20000), (k, j, outliers)             # sign-flip entries: observed 0-3 of 935 600; a race corrupts thousands
+            assert d.max() <= 2.0 * LR * STEPS, (k, j, d.max().item())          # ... and each moves by at most +-lr per step
 
 
 def test_unbounded_scene_with_distortion_loss_trains_and_renders():

@@ -203,3 +203,39 @@ def test_mixed_feature_index_transformation_properties():
             x = (v.double() - 0.5) / lv["scale"]
             nearest = torch.floor(x * canon["scale"] + 0.5 + 0.5).long()
             assert int((c - nearest).abs().max()) <= 1 and float((c == nearest).double().mean()) > 0.99
+
+
+def test_tcnn_torch_transliteration_matches_field_ref():
+    """oracle/tcnn_torch.py (the `tinycudann` stand-in of bench.py's gpu_reference leg) against oracle/field_ref.py: same layout,
+    hash, interpolation, SH and MLP semantics -> forward within fp16 rounding, parameter gradients within fp16 activation noise"""
+    import torch
+    from oracle import field_ref as fr
+    from oracle import tcnn_torch as tt
+    scale, T = 0.5, 12
+    b = float(np.exp(np.log(2048 * scale / 16) / 15))
+    enc = tt.NetworkWithInputEncoding(3, 16, {"otype": "HashGrid", "type": "Hash", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": T,
+                                              "base_resolution": 16, "n_tables": 1, "per_level_scale": b, "interpolation": "Linear"},
+                                      {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None", "n_neurons": 64, "n_hidden_layers": 1})
+    direnc = tt.Encoding(3, {"otype": "SphericalHarmonics", "degree": 4})
+    rgbnet = tt.Network(32, 3, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid", "n_neurons": 64, "n_hidden_layers": 2})
+    with torch.no_grad():
+        enc.params[3072:].uniform_(-0.5, 0.5, generator=torch.Generator().manual_seed(0))
+    ref = fr.NGPRef(scale, log2_T=T, params=(enc.params.detach(), rgbnet.params.detach()))
+    assert ref.xyz_params.numel() == enc.params.numel() and ref.rgb_params.numel() == rgbnet.params.numel()
+    g = torch.Generator().manual_seed(1)
+    N = 600
+    x = (torch.rand(N, 3, generator=g) - 0.5) * 2 * scale
+    d = torch.randn(N, 3, generator=g)
+    h = enc((x + scale) / (2 * scale))
+    sig = torch.exp(h[:, 0].float())
+    dn = d / torch.norm(d, dim=1, keepdim=True)
+    rgb = rgbnet(torch.cat([direnc((dn + 1) / 2), h], 1)).float()
+    sig_r, rgb_r = ref(x, d)
+    torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=1e-3)
+    torch.testing.assert_close(rgb, rgb_r, rtol=2e-2, atol=3e-3)
+    gs, gc = torch.randn(N, generator=g), torch.randn(N, 3, generator=g)
+    ((sig * gs).sum() + (rgb * gc).sum()).backward()
+    ((sig_r * gs).sum() + (rgb_r * gc).sum()).backward()
+    for got, want in ((enc.params.grad, ref.xyz_params.grad), (rgbnet.params.grad, ref.rgb_params.grad)):
+        sc = want.abs().max().item()
+        assert (got - want).abs().max().item() <= 3e-2 * sc
