@@ -233,10 +233,10 @@ def python_layer_arm(kind, dev, pool_dev, steps, warmup):
 
         def step():
             s = state["step"]
-            if s % 16 == 0:                                                             # train.py:165-168
-                model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=s < 256, erode=False)
             b = pool_dev[s % pool_dev.shape[0]]
-            with torch.autocast("cuda", dtype=torch.float16):
+            with torch.autocast("cuda", dtype=torch.float16):                            # Lightning precision=16 wraps the whole training_step
+                if s % 16 == 0:                                                         # train.py:165-168
+                    model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=s < 256, erode=False)
                 res = rendering.render(model, b[0], b[1], test_time=False, random_bg=False)
                 ld = loss_fn(res, {"rgb": b[2]})
                 loss = sum(v.mean() for v in ld.values())
@@ -456,6 +456,22 @@ def run_ours(args):
                 roofline = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": traffic,
                             "peak_source": pk["src"], "launch_us": breakdown[top], "algorithmic_per_launch": work, "samples_per_launch": mean_s}
 
+    # ---- the two table kernels against the on-chip rooflines they are actually bound by ("for T <= 2^20 report achieved L2
+    #      GB/s against a builder-measured random-32-B-sector L2 peak"): tools/l2_bench.cu -> profiles/l2_peaks_r02.json.  Algorithmic
+    #      sector requests per sample: 16 levels x 4 (y,z) corner pairs (the x-neighbours of a pair share a sector 7 times out of 8).
+    l2_roofline = None
+    if rank == 0 and breakdown:
+        try:
+            lp = json.load(open(os.path.join(ROOT, "profiles", "l2_peaks_r02.json")))["_summary"]
+            sectors = 64.0 * mean_s
+            l2_roofline = {"sectors_per_sample": 64, "samples_per_launch": mean_s, "peak_source": "profiles/l2_peaks_r02.json (tools/l2_bench.cu, measured on B200)"}
+            for kname, key, label in (("field_fwd", "l1_divergent_sector_peak_Gsectors_per_s", "gather"), ("grid_encode_bwd", "l2_red_v2_f32_peak_Gsectors_per_s", "red")):
+                if kname in breakdown:
+                    ach = sectors / (breakdown[kname] * 1e-6) / 1e9
+                    l2_roofline[kname] = {"kind": label, "achieved_Gsectors_per_s": ach, "peak_Gsectors_per_s": lp[key], "frac": ach / lp[key], "launch_us": breakdown[kname]}
+        except Exception:
+            l2_roofline = None
+
     # ---- 800x800 test-time render (second half of the metric), on the trained state
     # ---- 800x800 test-time render (second half of the metric), on the trained state.  N > 1: every rank renders its tile of image rows
     #      (mfnerf_b200.dist.tile_rows, no collective); a frame's time is its slowest rank's
@@ -506,7 +522,7 @@ def run_ours(args):
             "samples_per_sec": samples_dev / (ms_dev * 1e-3), "samples_per_ray": samples_dev / rays_total,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(3 * R * 3 * 4), "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K,
                     "api": "NGPEngine.train_step_packed(host_pinned_batch) -> C ABI; loss copied to pinned host memory every step"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "frozen_api": frozen, "render": render,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "l2_roofline": l2_roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "frozen_api": frozen, "render": render,
             "final_loss_terms": final_loss,
         }
         print(json.dumps(line), flush=True)

@@ -193,6 +193,12 @@ int64_t mfn_grid_layout(const mfn_grid_cfg* cfg_host, uint32_t* offsets_host, ui
 int mfn_grid_encode_fwd(const float* x01, const void* table, const mfn_grid_cfg* cfg_host, int64_t n, void* out, void* stream);
 /* dL_dout (n, L*F) fp16; dgrid fp32 (entries*F), ACCUMULATED into with atomics (caller zeroes it) */
 int mfn_grid_encode_bwd(const float* x01, const void* dL_dout, const mfn_grid_cfg* cfg_host, int64_t n, float* dgrid, void* stream);
+/* gradient w.r.t. the sample position (the reference's --optimize_ext path, custom_functions.py:102-112 / train.py:91,122,138; tcnn
+ * kernel_grid_backward_input): dL_dout (n, L*F) fp16 -> dx01 (n,3) f32 = sum_l dL_dout_l . d feat_l / d x01 (same scale as dL_dout) */
+int mfn_grid_encode_bwd_input(const float* x01, const void* table, const void* dL_dout, const mfn_grid_cfg* cfg_host, int64_t n, float* dx01,
+                              void* stream);
+/* gradient of the SH encoding w.r.t. dirs01: dL_dout (n,16) fp16 -> ddirs01 (n,3) f32 */
+int mfn_sh4_bwd(const float* dirs01, const void* dL_dout, int64_t n, float* ddirs01, void* stream);
 /* degree-4 spherical harmonics of 2*d01-1: (n,3) f32 -> 16 fp16 values written at out[i*out_stride + out_offset ...] */
 int mfn_sh4_fwd(const float* dirs01, int64_t n, void* out, int out_stride, int out_offset, void* stream);
 

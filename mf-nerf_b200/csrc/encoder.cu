@@ -296,7 +296,13 @@ grid_scatter_pair_kernel(const float4* __restrict__ x01, int n_max, const int32_
         if (head) {
             const uint32_t cx = gx + xb;
             uint32_t idx[4];
-            if (hashed) {
+            if (m.mixed) {   // MixedFeature: hash of the canonical-grid vertices (always hashed, table of 2^T entries)
+                const float r = m.canon[l];
+                const uint32_t ccx = canon_vertex(cx, r);
+                const uint32_t hy0 = canon_vertex(gy, r) * 2654435761u, hy1 = canon_vertex(gy + 1u, r) * 2654435761u;
+                const uint32_t hz0 = canon_vertex(gz, r) * 805459861u, hz1 = canon_vertex(gz + 1u, r) * 805459861u;
+                idx[0] = (ccx ^ hy0 ^ hz0) & mask; idx[1] = (ccx ^ hy1 ^ hz0) & mask; idx[2] = (ccx ^ hy0 ^ hz1) & mask; idx[3] = (ccx ^ hy1 ^ hz1) & mask;
+            } else if (hashed) {
                 const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
                 idx[0] = (cx ^ hy0 ^ hz0) & mask; idx[1] = (cx ^ hy1 ^ hz0) & mask; idx[2] = (cx ^ hy0 ^ hz1) & mask; idx[3] = (cx ^ hy1 ^ hz1) & mask;
             } else {
@@ -329,6 +335,79 @@ __global__ void sh4_fwd_kernel(const float* __restrict__ d01, int64_t n, __half*
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)i * out_stride + out_offset);
     dst[0] = reinterpret_cast<const uint4*>(h)[0];
     dst[1] = reinterpret_cast<const uint4*>(h)[1];
+}
+
+// Gradient w.r.t. the sample POSITION (the reference's --optimize_ext path: custom_functions.py:102-112 sums dL/dxyz over each ray's
+// samples into dL/drays_o, dL/drays_d; tcnn: kernel_grid_backward_input).  Trilinear interpolation is piecewise linear in x:
+//   d f_l / dx = scale_l * sum_{cy,cz} w_y(cy) w_z(cz) (v[x1,cy,cz] - v[x0,cy,cz])       (same for y, z)
+// dx01 = sum over levels and features of dL_dout[l][f] * d f_l[f] / dx.  One thread per sample, fp32 accumulation.
+template <int F>
+__global__ void __launch_bounds__(128)
+grid_encode_bwd_input_kernel(const __grid_constant__ EncArgs e, const __half* __restrict__ table, const __half* __restrict__ dL_dout,
+                             const __grid_constant__ GridMeta m, float* __restrict__ dx01) {
+    const int64_t n = e.n_max;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x, y, z;
+        load_pos(e, i, x, y, z);
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        for (int l = 0; l < m.n_levels; ++l) {
+            float g[F];
+            bool live = false;
+#pragma unroll
+            for (int f = 0; f < F; ++f) { g[f] = __half2float(dL_dout[(size_t)i * m.n_levels * F + l * F + f]); live |= (g[f] != 0.f); }
+            if (!live) continue;
+            const float s = m.scale[l];
+            const uint32_t res = m.res[l], size = m.size[l];
+            const bool hashed = (m.hashed >> l) & 1u;
+            const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+            const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+            const float wx = px - fx, wy = py - fy, wz = pz - fz;
+            const uint32_t cx0 = (uint32_t)(int)fx, cy0 = (uint32_t)(int)fy, cz0 = (uint32_t)(int)fz;
+            uint32_t cx[2] = {cx0, cx0 + 1u}, cy[2] = {cy0, cy0 + 1u}, cz[2] = {cz0, cz0 + 1u};
+            if (m.mixed) {
+                const float r = m.canon[l];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { cx[k] = canon_vertex(cx[k], r); cy[k] = canon_vertex(cy[k], r); cz[k] = canon_vertex(cz[k], r); }
+            }
+            const typename FeatVec<F>::T* lvl = reinterpret_cast<const typename FeatVec<F>::T*>(table) + m.offset[l];
+            float d[8];   // d[c] = <dL_dout_l, v_c>
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const typename FeatVec<F>::T raw = __ldg(lvl + grid_index(cx[c & 1], cy[(c >> 1) & 1], cz[c >> 2], res, size, hashed));
+                const __half* h = reinterpret_cast<const __half*>(&raw);
+                float acc = 0.f;
+#pragma unroll
+                for (int f = 0; f < F; ++f) acc = fmaf(g[f], __half2float(h[f]), acc);
+                d[c] = acc;
+            }
+            const float ux = 1.f - wx, uy = 1.f - wy, uz = 1.f - wz;
+            // corner c = x | y << 1 | z << 2
+            gx = fmaf(s, uy * uz * (d[1] - d[0]) + wy * uz * (d[3] - d[2]) + uy * wz * (d[5] - d[4]) + wy * wz * (d[7] - d[6]), gx);
+            gy = fmaf(s, ux * uz * (d[2] - d[0]) + wx * uz * (d[3] - d[1]) + ux * wz * (d[6] - d[4]) + wx * wz * (d[7] - d[5]), gy);
+            gz = fmaf(s, ux * uy * (d[4] - d[0]) + wx * uy * (d[5] - d[1]) + ux * wy * (d[6] - d[2]) + wx * wy * (d[7] - d[3]), gz);
+        }
+        dx01[3 * i] = gx; dx01[3 * i + 1] = gy; dx01[3 * i + 2] = gz;
+    }
+}
+
+// d SH4(2 d01 - 1) / d d01 contracted with dL_dout (n,16) fp16 -> (n,3) f32   (--optimize_ext: gradient w.r.t. the view direction)
+__global__ void sh4_bwd_kernel(const float* __restrict__ d01, const __half* __restrict__ dL_dout, int64_t n, float* __restrict__ dd01) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = fmaf(d01[3 * i], 2.f, -1.f), y = fmaf(d01[3 * i + 1], 2.f, -1.f), z = fmaf(d01[3 * i + 2], 2.f, -1.f);
+    float g[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) g[k] = __half2float(dL_dout[(size_t)i * 16 + k]);
+    const float c1 = 0.48860251190291987f, c2 = 1.0925484305920792f, c3 = 0.94617469575755997f, c5 = 0.54627421529603959f, c6 = 0.59004358992664352f,
+                c7 = 2.8906114426405538f, c8 = 0.45704579946446572f, c9 = 0.3731763325901154f, c10 = 1.4453057213202769f;
+    const float x2 = x * x, y2 = y * y, z2 = z * z;
+    const float gx = -c1 * g[3] + c2 * y * g[4] - c2 * z * g[7] + 2.f * c5 * x * g[8] - 6.f * c6 * x * y * g[9] + c7 * y * z * g[10] + c8 * (1.f - 5.f * z2) * g[13] +
+                     2.f * c10 * x * z * g[14] + c6 * (-3.f * x2 + 3.f * y2) * g[15];
+    const float gy = -c1 * g[1] + c2 * x * g[4] - c2 * z * g[5] - 2.f * c5 * y * g[8] + c6 * (-3.f * x2 + 3.f * y2) * g[9] + c7 * x * z * g[10] +
+                     c8 * (1.f - 5.f * z2) * g[11] - 2.f * c10 * y * z * g[14] + 6.f * c6 * x * y * g[15];
+    const float gz = c1 * g[2] - c2 * y * g[5] + 2.f * c3 * z * g[6] - c2 * x * g[7] + c7 * x * y * g[10] - 10.f * c8 * y * z * g[11] + c9 * (15.f * z2 - 3.f) * g[12] -
+                     10.f * c8 * x * z * g[13] + c10 * (x2 - y2) * g[14];
+    dd01[3 * i] = 2.f * gx; dd01[3 * i + 1] = 2.f * gy; dd01[3 * i + 2] = 2.f * gz;      // v = 2 d01 - 1
 }
 
 }  // namespace mfn
@@ -412,4 +491,24 @@ extern "C" int mfn_sh4_fwd(const float* dirs01, int64_t n, void* out, int out_st
     if (!dirs01 || !out) { set_error("mfn_sh4_fwd: null pointer"); return MFN_ERR_ARG; }
     sh4_fwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs01, n, (__half*)out, out_stride, out_offset);
     return check_launch("mfn_sh4_fwd", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_grid_encode_bwd_input(const float* x01, const void* table, const void* dL_dout, const mfn_grid_cfg* cfg, int64_t n, float* dx01, void* stream) {
+    GridMeta m;
+    int rc = build_grid_meta(cfg, &m, "mfn_grid_encode_bwd_input");
+    if (rc != MFN_OK) return rc;
+    if (n < 0) { set_error("mfn_grid_encode_bwd_input: bad n"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!x01 || !table || !dL_dout || !dx01) { set_error("mfn_grid_encode_bwd_input: null pointer"); return MFN_ERR_ARG; }
+    EncArgs e{}; e.x = x01; e.normalize = false; e.n_max = n; e.n_dev = nullptr;
+    MFN_F_DISPATCH(cfg->n_features, (grid_encode_bwd_input_kernel<F><<<enc_grid(n, 128, 16), 128, 0, (cudaStream_t)stream>>>(e, (const __half*)table, (const __half*)dL_dout, m, dx01));)
+    return check_launch("mfn_grid_encode_bwd_input", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_sh4_bwd(const float* dirs01, const void* dL_dout, int64_t n, float* ddirs01, void* stream) {
+    if (n < 0) { set_error("mfn_sh4_bwd: bad argument"); return MFN_ERR_ARG; }
+    if (n == 0) return MFN_OK;
+    if (!dirs01 || !dL_dout || !ddirs01) { set_error("mfn_sh4_bwd: null pointer"); return MFN_ERR_ARG; }
+    sh4_bwd_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(dirs01, (const __half*)dL_dout, n, ddirs01);
+    return check_launch("mfn_sh4_bwd", (cudaStream_t)stream);
 }

@@ -240,6 +240,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.dfeats = (__half*)(ws + fw.dfeats);
         f.dfeats_stride = (n_max + 63) / 64 * 64;
         f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
+        { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         WgradReduce wr{};
         if ((rc = fused_field_backward(f, cfg->rgb_hidden, d_xyz_params, d_rgb_params, &wr, st)) != MFN_OK) return rc;
         return grid_scatter_level_major((const float4*)(ws + fw.x01), n_max, n_dev, f.dfeats, f.dfeats_stride, m, d_xyz_params + 64 * 32 + 16 * 64, wr, st);

@@ -128,16 +128,24 @@ __device__ __forceinline__ uint32_t gather_level(const uint32_t* __restrict__ ta
 // Lane-pair variant: the two lanes of a pair work on the same sample and each fetches the 4 corners of ITS x (gx + xb), so the
 // corners (x, x+1) of one (y, z) -- same 32-byte sector 7 times out of 8 -- are requested by the same load instruction: a warp's
 // gather touches <= 16 sectors instead of <= 32, and the L1 sector rate is what bounds this phase.  Returns the pair's sum.
+template <bool MIXED>
 __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb, uint64_t pol) {
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
+    const uint32_t res = m.res[l], off = m.offset[l], size = m.size[l];
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     const float wx = px - fx, wy = py - fy, wz = pz - fz;
     const uint32_t cx = (uint32_t)(int)fx + (uint32_t)xb, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
     const uint32_t* lvl = table + off;
     uint32_t idx[4];
-    if ((m.hashed >> l) & 1u) {
+    if (MIXED) {   // MixedFeature grid: vertices are hashed by their canonical-grid coordinates (grid_common.cuh: canon_vertex); the
+                   // lane pair still splits the x corners, it just no longer finds them in one sector
+        const float r = m.canon[l];
+        const uint32_t mask = size - 1u, ccx = canon_vertex(cx, r);
+        const uint32_t hy0 = canon_vertex(gy, r) * 2654435761u, hy1 = canon_vertex(gy + 1u, r) * 2654435761u;
+        const uint32_t hz0 = canon_vertex(gz, r) * 805459861u, hz1 = canon_vertex(gz + 1u, r) * 805459861u;
+        idx[0] = (ccx ^ hy0 ^ hz0) & mask; idx[1] = (ccx ^ hy1 ^ hz0) & mask; idx[2] = (ccx ^ hy0 ^ hz1) & mask; idx[3] = (ccx ^ hy1 ^ hz1) & mask;
+    } else if ((m.hashed >> l) & 1u) {
         const uint32_t mask = size - 1u;
         const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
         idx[0] = (cx ^ hy0 ^ hz0) & mask; idx[1] = (cx ^ hy1 ^ hz0) & mask; idx[2] = (cx ^ hy0 ^ hz1) & mask; idx[3] = (cx ^ hy1 ^ hz1) & mask;
@@ -215,7 +223,7 @@ constexpr bool kTrainAlias = true;      // training mode too: one tile region, e
 // phase timestamps of CTA 0 (tools/fwd_phases.py): a.dbg != nullptr only in that tool
 #define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
 
-template <int NH2, int MODE>
+template <int NH2, int MODE, bool MIXED>
 __global__ void __launch_bounds__(kFwdThreads, ((MODE == 1 || MODE == 4) && !kTrainAlias) ? 4 : 5)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
     constexpr bool TRAIN = (MODE == 1 || MODE == 4), FULL = (MODE == 4), RGB = (MODE < 2 || MODE == 4);
@@ -270,7 +278,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             }
 #pragma unroll 2
             for (int l = 0; l < 16; ++l) {
-                const uint32_t v = gather_level_pair(table, m, l, x, y, z, xb, pol_keep);    // (invalid rows gather entry 0 harmlessly)
+                const uint32_t v = gather_level_pair<MIXED>(table, m, l, x, y, z, xb, pol_keep);    // (invalid rows gather entry 0 harmlessly)
                 if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + oX + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
             }
         }
@@ -442,6 +450,8 @@ __device__ __forceinline__ void mask_epilogue32(uint32_t taddr, unsigned char* t
 
 // RC = true: only the X tile was saved; H1, h, CAT, H2, H3 are recomputed here (four more MMAs + epilogues per tile, nothing read
 // from HBM but 64 + 12 + 8 B/sample).  RC = false: round 1's path, the five tiles come back as one 64 KiB bulk copy.
+// phase timestamps of CTA 0 / thread 0 of the backward kernel (tools/fwd_phases.py): after every MMA-completion wait and every barrier
+#define MFN_BTS() do { if (a.dbg && blockIdx.x == 0 && tid == 0 && tile_no < 6 && ts_k < 40) a.dbg[256 + tile_no * 40 + (ts_k++)] = clock64(); } while (0)
 template <int NH2, bool RC>
 __global__ void __launch_bounds__(kBwdThreads, 2)
 field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
@@ -471,7 +481,10 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     uint32_t acc = 0;                                              // 0 on the CTA's first tile: weight-gradient MMAs overwrite
     bool bad = false;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tile_no = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
+        int ts_k = 0;
+        MFN_BTS();
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
         if (tid == 0) {   // RC: the saved X tile; else the whole activation blob of this tile -- one bulk async copy either way
@@ -509,7 +522,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         mbar_wait(&bar_load, ph_load); ph_load ^= 1u;
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); MFN_BTS();
         if (RC) {
             // ---- recomputed forward: H1 = relu(X.W1^T) ; h = H1.W2^T -> CAT[:, 16:32] ; H2 = relu(CAT.W3^T) ; H3 = relu(H2.W4^T)
             if (tid == 0) {
@@ -519,12 +532,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
                 for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sX, 32, k0), desc_kmajor(sbase + kW1, 32, k0), id, k0 > 0);
                 mma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
             tc_fence_after();
             relu_epilogue32(trow + kAccH, sBlob + kBH1, row, 32 * hsel);
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads(); MFN_BTS();
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t id = idesc_f16(128, 16, false, false);
@@ -532,7 +545,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
                 for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccO2, desc_kmajor(sH1, 64, k0), desc_kmajor(sbase + kW2, 64, k0), id, k0 > 0);
                 mma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
             tc_fence_after();
             if (hsel == 0) {
                 uint32_t r[16];
@@ -548,7 +561,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             }
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads(); MFN_BTS();
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t id = idesc_f16(128, 64, false, false);
@@ -556,12 +569,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
                 for (int k0 = 0; k0 < 32; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sC, 32, k0), desc_kmajor(sbase + kW3, 32, k0), id, k0 > 0);
                 mma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
             tc_fence_after();
             relu_epilogue32(trow + kAccH, sBlob + kBH2, row, 32 * hsel);
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads(); MFN_BTS();
             if (NH2 == 2) {
                 if (tid == 0) {
                     tc_fence_after();
@@ -570,12 +583,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
                     for (int k0 = 0; k0 < 64; k0 += 16) mma_f16_ss(tbase + kAccH, desc_kmajor(sH2, 64, k0), desc_kmajor(sbase + kW4, 64, k0), id, k0 > 0);
                     mma_commit(&bar_mma);
                 }
-                mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+                mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
                 tc_fence_after();
                 relu_epilogue32(trow + kAccH, sBlob + kBH3, row, 32 * hsel);
                 fence_async_smem();
                 tc_fence_before();
-                __syncthreads();
+                __syncthreads(); MFN_BTS();
             }
         }
         // ---- stage A: dH_last = dZ5 . W5 ;  dW5^T += H_last^T . dZ5
@@ -587,12 +600,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW5, desc_mnmajor(sHL, 64, k0), desc_mnmajor(sDZo, 16, k0), idw, acc | (k0 > 0));
             mma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
         tc_fence_after();
         mask_epilogue32(trow + kAccH, pHL, row, 32 * hsel);                 // dZ of the last hidden layer, in place
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); MFN_BTS();
         if (NH2 == 2) {
             // ---- stage B: dH2 = dZ4 . W4 ;  dW4^T += H2^T . dZ4
             if (tid == 0) {
@@ -605,12 +618,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
                 for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW4, desc_mnmajor(sH2, 64, k0), desc_mnmajor(sH3, 64, k0), idw, acc | (k0 > 0));
                 mma_commit(&bar_mma);
             }
-            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+            mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
             tc_fence_after();
             mask_epilogue32(trow + kAccH, sBlob + kBH2, row, 32 * hsel);    // dZ3 in place of H2
             fence_async_smem();
             tc_fence_before();
-            __syncthreads();
+            __syncthreads(); MFN_BTS();
         }
         // ---- stage C: dCAT = dZ3 . W3 (32 columns) ;  dW3 += dZ3^T . CAT
         if (tid == 0) {
@@ -623,7 +636,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW3, desc_mnmajor(sH2, 64, k0), desc_mnmajor(sC, 32, k0), idw, acc | (k0 > 0));
             mma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
         tc_fence_after();
         if (hsel == 0) {   // dh = dCAT[:, 16:32] ; dh[0] += loss_scale * dL/dsigma * exp(clamp(h0, -15, 15))   (TruncExp backward)
             uint32_t r[16];
@@ -645,7 +658,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); MFN_BTS();
         // ---- stage D: dH1 = dZ2 . W2 ;  dW2^T += H1^T . dZ2
         if (tid == 0) {
             tc_fence_after();
@@ -655,12 +668,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW2, desc_mnmajor(sH1, 64, k0), desc_mnmajor(sDZo, 16, k0), idw, acc | (k0 > 0));
             mma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
         tc_fence_after();
         mask_epilogue32(trow + kAccH, sBlob + kBH1, row, 32 * hsel);        // dZ1 in place of H1
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); MFN_BTS();
         // ---- stage E: dX = dZ1 . W1 (32 columns) ;  dW1 += dZ1^T . X
         if (tid == 0) {
             tc_fence_after();
@@ -672,7 +685,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             for (int k0 = 0; k0 < kFT; k0 += 16) mma_f16_ss(tbase + kAccW1, desc_mnmajor(sH1, 64, k0), desc_mnmajor(sX, 32, k0), idw, acc | (k0 > 0));
             mma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u;
+        mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS();
         tc_fence_after();
         {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel; each thread of a row does 8 levels
             uint32_t r[16];
@@ -693,7 +706,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         acc = 1u;
         fence_async_smem();   // generic reads/writes of the tile area are ordered before the next bulk copy into it
         tc_fence_before();
-        __syncthreads();
+        __syncthreads(); MFN_BTS();
     }
     if (bad && a.overflow) *a.overflow = 1;
     // ---- flush this CTA's weight-gradient accumulators (M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16)
@@ -745,7 +758,7 @@ static int num_sms() {
 }
 
 bool fused_field_supported(const mfn_field_cfg* c) {
-    return c->grid.grid_type == MFN_GRID_HASH && c->grid.n_levels == 16 && c->grid.n_features == 2 && c->sigma_width == 64 && c->sigma_hidden == 1 && c->rgb_width == 64 &&
+    return (c->grid.grid_type == MFN_GRID_HASH || c->grid.grid_type == MFN_GRID_MIXED) && c->grid.n_levels == 16 && c->grid.n_features == 2 && c->sigma_width == 64 && c->sigma_hidden == 1 && c->rgb_width == 64 &&
            (c->rgb_hidden == 1 || c->rgb_hidden == 2);
 }
 int fused_bwd_max_ctas() { return 2 * num_sms(); }
@@ -758,17 +771,21 @@ bool fused_save_full() {
 size_t fused_blob_bytes(int64_t n_max) { return (size_t)ceil_div(n_max, kFT) * (fused_save_full() ? kBlob : kBlobX); }
 size_t fused_partial_bytes() { return (size_t)fused_bwd_max_ctas() * kNumWg * sizeof(float); }
 
-template <int NH2, int MODE>
-static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
+template <int NH2, int MODE, bool MIXED>
+static void launch_fwd_m(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
     constexpr int smem_bytes = ((MODE == 1 || MODE == 4) && !kTrainAlias) ? kFwdSmem : kFwdX + kFT * 64 * 2;      // one shared tile region
     constexpr int max_ctas = ((MODE == 1 || MODE == 4) && !kTrainAlias) ? 4 : 5;
-    static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), true);
+    static bool once = (cudaFuncSetAttribute(field_fwd_fused_kernel<NH2, MODE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) { const char* e = getenv("MFN_FWD_CTAS"); ctas_per_sm = e ? atoi(e) : max_ctas; if (ctas_per_sm < 1 || ctas_per_sm > max_ctas) ctas_per_sm = max_ctas; }
     const int64_t cap = ctas_per_sm * (int64_t)num_sms();
-    field_fwd_fused_kernel<NH2, MODE><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(a, m);
+    field_fwd_fused_kernel<NH2, MODE, MIXED><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(a, m);
+}
+template <int NH2, int MODE>
+static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
+    if (m.mixed) launch_fwd_m<NH2, MODE, true>(a, m, st); else launch_fwd_m<NH2, MODE, false>(a, m, st);
 }
 
 // mode: 0 inference, 1 training, 2 density only, 3 raw 16 outputs of the sigma network

@@ -65,6 +65,21 @@ def grid_encode_bwd(x01, dL_dout_h, cfg, dgrid_f32):
         call("mfn_grid_encode_bwd", ptr(x01), ptr(dL_dout_h), ctypes.byref(cfg), x01.shape[0], ptr(dgrid_f32), stream_ptr(x01.device))
 
 
+def grid_encode_bwd_input(x01, table_h, dL_dout_h, cfg):
+    """gradient w.r.t. the positions: dL_dout (n, L*F) fp16 -> (n,3) f32, same scale as dL_dout"""
+    dx = torch.empty(x01.shape[0], 3, dtype=torch.float32, device=x01.device)
+    with _dev_guard(x01):
+        call("mfn_grid_encode_bwd_input", ptr(x01), ptr(table_h), ptr(dL_dout_h), ctypes.byref(cfg), x01.shape[0], ptr(dx), stream_ptr(x01.device))
+    return dx
+
+
+def sh4_bwd(d01, dL_dout_h):
+    dd = torch.empty(d01.shape[0], 3, dtype=torch.float32, device=d01.device)
+    with _dev_guard(d01):
+        call("mfn_sh4_bwd", ptr(d01), ptr(dL_dout_h), d01.shape[0], ptr(dd), stream_ptr(d01.device))
+    return dd
+
+
 def sh4_fwd(d01, out=None, out_offset=0):
     n = d01.shape[0]
     if out is None:

@@ -120,11 +120,21 @@ class Network(nn.Module):
 class _ShFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return F.sh4_fwd(x.float().contiguous())
+        xf = x.float().contiguous()
+        ctx.save_for_backward(xf)
+        ctx.x_dtype = x.dtype
+        return F.sh4_fwd(xf)
 
     @staticmethod
     def backward(ctx, dout):
-        raise NotImplementedError("gradient w.r.t. view directions (--optimize_ext) is not implemented")
+        # gradient w.r.t. the view direction: the reference's --optimize_ext path (custom_functions.py:102-112, train.py:91,122,138)
+        (xf,) = ctx.saved_tensors
+        return F.sh4_bwd(xf, dout.to(torch.float16).contiguous()).to(ctx.x_dtype)
+
+
+def _grid_input_grad(xf, table_h, dfeats_h, mod, x_dtype):
+    """dL/dx01 from the (loss-scaled, fp16) gradient of the encoded features -- the --optimize_ext path"""
+    return (F.grid_encode_bwd_input(xf, table_h, dfeats_h, mod.grid_cfg) / mod.loss_scale).to(x_dtype)
 
 
 class _GridFn(torch.autograd.Function):
@@ -134,19 +144,22 @@ class _GridFn(torch.autograd.Function):
         ph = mod._cache.get(params)
         feats = F.grid_encode_fwd(xf, ph, mod.grid_cfg)
         ctx.mod = mod
-        ctx.save_for_backward(xf)
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xf, ph)
         return feats
 
     @staticmethod
     def backward(ctx, dout):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. sample positions (--optimize_ext) is not implemented")
         mod = ctx.mod
-        (xf,) = ctx.saved_tensors
-        dgrid = torch.zeros(mod.params.shape[0], dtype=torch.float32, device=xf.device)
-        F.grid_encode_bwd(xf, (dout.float() * mod.loss_scale).to(torch.float16).contiguous(), mod.grid_cfg, dgrid)
-        dgrid /= mod.loss_scale
-        return None, dgrid, None
+        xf, ph = ctx.saved_tensors
+        d16 = (dout.float() * mod.loss_scale).to(torch.float16).contiguous()
+        dgrid = None
+        if ctx.needs_input_grad[1]:
+            dgrid = torch.zeros(mod.params.shape[0], dtype=torch.float32, device=xf.device)
+            F.grid_encode_bwd(xf, d16, mod.grid_cfg, dgrid)
+            dgrid /= mod.loss_scale
+        dx = _grid_input_grad(xf, ph, d16, mod, ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        return dx, dgrid, None
 
 
 def _parse_grid(cfg):
@@ -196,13 +209,12 @@ class _EncMlpFn(torch.autograd.Function):
         feats = F.grid_encode_fwd(xf, table, mod.grid_cfg)
         out, acts = F.mlp_fwd(feats, w_mlp, mod.n_enc_out, mod.width, mod.n_hidden, mod.out_act, save_acts=True)
         ctx.mod = mod
+        ctx.x_dtype = x.dtype
         ctx.save_for_backward(xf, feats, acts, out, ph)
         return out[:, :mod.n_output_dims]
 
     @staticmethod
     def backward(ctx, dout):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. sample positions (--optimize_ext) is not implemented")
         mod = ctx.mod
         xf, feats, acts, out, ph = ctx.saved_tensors
         n = xf.shape[0]
@@ -213,7 +225,8 @@ class _EncMlpFn(torch.autograd.Function):
                            dparams[:mod.n_mlp_params], need_dx=True)
         F.grid_encode_bwd(xf, dfeats, mod.grid_cfg, dparams[mod.n_mlp_params:])
         dparams /= mod.loss_scale
-        return None, dparams, None
+        dx = _grid_input_grad(xf, ph[mod.n_mlp_params:], dfeats, mod, ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        return dx, dparams, None
 
 
 class NetworkWithInputEncoding(nn.Module):

@@ -41,14 +41,18 @@ def _grad_close(got, want, name, big_frac=5e-2, rtol=8e-2, max_frac=3e-2):
     assert err.max().item() <= max_frac * sc, (name, err.max().item(), sc)
 
 
-def test_field_fwd_bwd_vs_restatement():
+@pytest.mark.parametrize("grid,n_tables", [("Hash", 1), ("MixedFeature", 8), ("MixedFeature", 3)])
+def test_field_fwd_bwd_vs_restatement(grid, n_tables):
+    """the fused tcgen05 field kernels (mfn_field_fwd / mfn_field_bwd, what the engine's training step runs) against the torch
+    restatement, for the plain hash grid and for the fork's MixedFeature grid (--grid MixedFeature --N_tables K)"""
     import ctypes
-    from mfnerf_b200._lib import call, ptr, stream_ptr
-    eng = _engine()
+    from mfnerf_b200._lib import call, ptr, stream_ptr, lib
+    eng = _engine(grid=grid, n_tables=n_tables)
+    assert lib.mfn_field_is_fused(ctypes.byref(eng.cfg)) == 1 and eng._fused
     with torch.no_grad():
         eng.params[eng.n_mlp1:eng.n_xyz].uniform_(-0.5, 0.5)     # make the grid features matter
         eng.params_h.copy_(eng.params)
-    ref = fr.NGPRef(0.5, log2_T=15, params=(eng.params[:eng.n_xyz].cpu(), eng.params[eng.off_rgb:eng.off_rgb + eng.n_rgb].cpu())).cuda()
+    ref = fr.NGPRef(0.5, log2_T=15, grid=grid, n_tables=n_tables, params=(eng.params[:eng.n_xyz].cpu(), eng.params[eng.off_rgb:eng.off_rgb + eng.n_rgb].cpu())).cuda()
     g = torch.Generator().manual_seed(5)
     N = 3001
     x = ((torch.rand(N, 3, generator=g) - 0.5)).cuda(); d = torch.randn(N, 3, generator=g).cuda()
@@ -138,6 +142,59 @@ def test_train_step_matches_reference_python_layer(capsys):
     assert eng.overflow.item() == 0
     _grad_close(eng.grads[:eng.n_xyz] / 128.0, model.xyz_encoder.params.grad, "xyz")
     _grad_close(eng.grads[eng.off_rgb:eng.off_rgb + eng.n_rgb] / 128.0, model.rgb_net.params.grad, "rgb")
+
+
+def test_ray_gradients_through_the_reference_python_layer():
+    """SURVEY 8(a) row a5, end to end: with --optimize_ext the reference back-propagates into the camera poses through
+    RayMarcher.backward (custom_functions.py:102-112: segment_csr of dL/dxyz and dL/dxyz * t + dL/ddir per ray).  The reference's
+    unmodified rendering.py / custom_functions.py run on the drop-ins with rays that require grad; dL/drays_o and dL/drays_d are
+    compared with plain-torch autograd of the same pipeline (samples o + t d at the marcher's t, oracle/field_ref.py field, a
+    torch restatement of volumerendering.cu:6-85 with its early termination).  Tolerance: fp16 field + fp16 gradient transport,
+    8 % on the large entries, 3 % of the largest elsewhere (the parameter-gradient tolerance of this file)."""
+    rendering, networks, losses = _load_reference_python()
+    R = 96
+    eng = _engine(R)
+    with torch.no_grad():
+        eng.params[eng.n_mlp1:eng.n_xyz].uniform_(-0.3, 0.3)
+    model = networks.NGP(scale=0.5, hparams=_hparams(), rgb_act="Sigmoid").cuda()
+    with torch.no_grad():
+        model.xyz_encoder.params.copy_(eng.params[:eng.n_xyz]); model.rgb_net.params.copy_(eng.params[eng.off_rgb:eng.off_rgb + eng.n_rgb])
+        model.density_bitfield.copy_(eng.density_bitfield)
+    sc = scenes.scene("lego", R, seed=13)
+    o = torch.from_numpy(sc["rays_o"]).cuda().requires_grad_(True); d = torch.from_numpy(sc["rays_d"]).cuda().requires_grad_(True)
+    tgt = torch.rand(R, 3, generator=torch.Generator().manual_seed(2)).cuda()
+    noise = torch.from_numpy(sc["noise"]).cuda()
+    real_rand_like = torch.rand_like
+    torch.rand_like = lambda t, *a, **k: noise.clone() if t.shape == noise.shape else real_rand_like(t, *a, **k)
+    try:
+        res = rendering.render(model, o, d, test_time=False, exp_step_factor=0.0)
+    finally:
+        torch.rand_like = real_rand_like
+    loss = sum(l.mean() for l in losses.NeRFLoss(lambda_distortion=0)(res, {"rgb": tgt}).values())
+    loss.backward()
+    assert o.grad is not None and d.grad is not None and o.grad.abs().max() > 0 and d.grad.abs().max() > 0
+    # ---- plain torch restatement, fp32 autograd
+    rays_a, ts, deltas = res["rays_a"].detach(), res["ts"].detach().float(), res["deltas"].detach().float()
+    ref = fr.NGPRef(0.5, log2_T=15, params=(model.xyz_encoder.params.detach().cpu(), model.rgb_net.params.detach().cpu())).cuda()
+    o2 = o.detach().clone().requires_grad_(True); d2 = d.detach().clone().requires_grad_(True)
+    ridx = torch.repeat_interleave(rays_a[:, 0], rays_a[:, 2])
+    assert int(rays_a[:, 2].sum()) == ts.shape[0] and torch.equal(rays_a[1:, 1], (rays_a[:-1, 1] + rays_a[:-1, 2]))   # segment_csr's layout assumption
+    xyzs = o2[ridx] + ts[:, None] * d2[ridx]
+    sig, rgb = ref(xyzs, d2[ridx])
+    out_rgb, out_op = [], []
+    for r in range(R):
+        s0, n = int(rays_a[r, 1]), int(rays_a[r, 2])
+        a = 1 - torch.exp(-sig[s0:s0 + n] * deltas[s0:s0 + n])
+        T = torch.cumprod(torch.cat([torch.ones(1, device="cuda"), 1 - a[:-1]]), 0) if n > 0 else a
+        w = a * T * (T > 1e-4)                                   # the sample that drives T below the threshold is still composited
+        out_op.append(w.sum()); out_rgb.append((w[:, None] * rgb[s0:s0 + n]).sum(0))
+    op = torch.stack(out_op); col = torch.stack(out_rgb) + (1 - op)[:, None]     # white background (exp_step_factor == 0)
+    oe = op + 1e-10
+    loss2 = ((col - tgt) ** 2).mean() + (1e-3 * -oe * torch.log(oe)).mean()
+    loss2.backward()
+    assert abs(loss.item() - loss2.item()) <= 2e-3 * abs(loss2.item()) + 1e-6
+    _grad_close(o.grad.float(), o2.grad, "dL/drays_o", big_frac=1e-1)
+    _grad_close(d.grad.float(), d2.grad, "dL/drays_d", big_frac=1e-1)
 
 
 def test_graph_replay_equals_eager_and_training_reduces_loss():
@@ -361,9 +418,11 @@ def test_other_rgb_net_shapes(rgb_channels, rgb_layers):
 
 
 def test_mixed_feature_grid_trains_and_renders():
-    """--grid MixedFeature --N_tables 8 (the fork's headline configuration) through the engine: unfused field kernels, per-op render loop"""
+    """--grid MixedFeature --N_tables 8 (the fork's headline configuration) through the engine: the fused tcgen05 field kernels and the
+    device-side wavefront renderer, like the plain hash grid"""
     from oracle import field_ref as fr
     eng = _engine(256, T=15, grid="MixedFeature", n_tables=8)
+    assert eng._fused and eng._fast_front
     assert eng.n_xyz == eng.n_mlp1 + 8 * (1 << 15) * 2
     rays = scenes.scene("lego", 256, seed=13)
     o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
@@ -385,9 +444,12 @@ def test_mixed_feature_grid_trains_and_renders():
         sig_r, rgb_r = ref(eng.xyzs[:n], eng.dirs[:n])
     torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=2e-3)
     torch.testing.assert_close(rgb, rgb_r, rtol=2e-2, atol=4e-3)
-    out = eng.render(o, d)                                  # dispatches to the per-op loop for shapes outside the fused kernels
+    out = eng.render(o, d)                                  # device-side wavefront (csrc/render.cu) on the fused field kernel
     assert out["rgb"].shape == (256, 3) and torch.isfinite(out["rgb"]).all() and int(out["total_samples"]) > 0
     assert float((out["rgb"] - tgt).abs().mean()) < 0.25
+    loop = eng.render_reference_loop(o, d)                  # the reference's loop, one launch per operation, same kernels
+    assert int(out["total_samples"]) == int(loop["total_samples"])
+    torch.testing.assert_close(out["rgb"], loop["rgb"], rtol=0, atol=1e-6)
 
 
 def test_checkpoint_round_trip_with_the_reference_loader(tmp_path):
