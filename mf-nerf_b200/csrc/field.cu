@@ -10,7 +10,7 @@
 
 namespace mfn {
 
-// MFN_FIELD_IMPL=v1 selects the unfused pipeline below (kept for shapes the fused kernels do not cover and for A/B measurements)
+// MFN_FIELD_IMPL=v1 selects the unfused mma.sync pipeline below (kept for A/B measurements; every shape field_cfg_ok accepts is fused)
 static bool use_fused(const mfn_field_cfg* c) {
     static int v1 = -1;
     if (v1 < 0) { const char* e = getenv("MFN_FIELD_IMPL"); v1 = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; }
@@ -19,14 +19,14 @@ static bool use_fused(const mfn_field_cfg* c) {
 
 // workspace of the fused path: [saved X tiles | rgb outputs (n,4) f16 | dfeats (n,32) f16 | weight-gradient partials | x01 (n,4) f32 | dirs (n,3) f32 | count]
 struct FusedWs { size_t blobs, rgb, dfeats, partials, x01, dirs, count, total; };
-static FusedWs fused_ws(int64_t n, bool training) {
+static FusedWs fused_ws(const mfn_field_cfg* c, int64_t n, bool training) {
     FusedWs w{};
     size_t o = 0;
     if (training) {
         w.blobs = o; o += fused_blob_bytes(n);
         w.rgb = o; o += (size_t)(n * 8 + 255) / 256 * 256;
         w.dfeats = o; o += (size_t)((n + 63) / 64 * 64) * 64;
-        w.partials = o; o += (fused_partial_bytes() + 255) / 256 * 256;
+        w.partials = o; o += (fused_partial_bytes(c->rgb_width) + 255) / 256 * 256;
         w.x01 = o; o += (size_t)(n * 16 + 255) / 256 * 256;
         w.dirs = o; o += (size_t)(n * 12 + 255) / 256 * 256;
         w.count = o; o += 256;         // int32: the sample count of the forward pass (mfn_field_count_ptr)
@@ -151,13 +151,13 @@ extern "C" int mfn_field_is_fused(const mfn_field_cfg* cfg) {
 
 extern "C" void* mfn_field_count_ptr(const mfn_field_cfg* cfg, void* workspace, int64_t n_max) {
     if (field_cfg_ok(cfg, "mfn_field_count_ptr") != MFN_OK || !workspace || n_max < 0 || !use_fused(cfg)) return nullptr;
-    return (char*)workspace + fused_ws(n_max, true).count;
+    return (char*)workspace + fused_ws(cfg, n_max, true).count;
 }
 
 extern "C" int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg, int64_t n_max, int training) {
     if (field_cfg_ok(cfg, "mfn_field_workspace_bytes") != MFN_OK || n_max < 0) return -1;
     const size_t v1 = field_ws(cfg, n_max, training != 0).total;
-    const size_t fz = fused_field_supported(cfg) ? fused_ws(n_max, training != 0).total : 0;
+    const size_t fz = fused_field_supported(cfg) ? fused_ws(cfg, n_max, training != 0).total : 0;
     return (int64_t)(v1 > fz ? v1 : fz);
 }
 
@@ -194,13 +194,13 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     char* ws = (char*)workspace;
     if (use_fused(cfg)) {
         // training layout when the workspace is large enough for it (the matching mfn_field_bwd reads it), inference otherwise
-        const FusedWs fw = fused_ws(n_max, true);
+        const FusedWs fw = fused_ws(cfg, n_max, true);
         const bool train = (size_t)workspace_bytes >= fw.total;
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, dirs, n_max, n_dev);
         f.sigmas = sigmas; f.rgbs = rgbs;
         if (train) { f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.x01 = (float4*)(ws + fw.x01); f.n_out = (int32_t*)(ws + fw.count); }
         { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
-        return fused_field_forward(f, m, cfg->rgb_hidden, train ? 1 : 0, st);
+        return fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, train ? 1 : 0, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;
@@ -234,7 +234,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)workspace;
     if (use_fused(cfg)) {
-        const FusedWs fw = fused_ws(n_max, true);
+        const FusedWs fw = fused_ws(cfg, n_max, true);
         if ((size_t)workspace_bytes < fw.total) { set_error("mfn_field_bwd: workspace too small"); return MFN_ERR_ARG; }
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, nullptr, n_max, n_dev);
         f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.dfeats = (__half*)(ws + fw.dfeats);
@@ -242,7 +242,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
         { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         WgradReduce wr{};
-        if ((rc = fused_field_backward(f, cfg->rgb_hidden, d_xyz_params, d_rgb_params, &wr, st)) != MFN_OK) return rc;
+        if ((rc = fused_field_backward(f, cfg->rgb_width, cfg->rgb_hidden, d_xyz_params, d_rgb_params, &wr, st)) != MFN_OK) return rc;
         return grid_scatter_level_major((const float4*)(ws + fw.x01), n_max, n_dev, f.dfeats, f.dfeats_stride, m, d_xyz_params + 64 * 32 + 16 * 64, wr, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;
@@ -279,7 +279,7 @@ extern "C" int mfn_geo_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h, c
     if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_geo_fwd")) != MFN_OK) return rc;
     FusedArgs f; make_fused(f, cfg, xyz_params_h, nullptr, xyzs, nullptr, n_max, n_dev);
     f.h_out = (__half*)h_out;
-    return fused_field_forward(f, m, cfg->rgb_hidden, 3, (cudaStream_t)stream);
+    return fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, 3, (cudaStream_t)stream);
 }
 
 extern "C" int mfn_density_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h, const float* xyzs, int64_t n_max, const int32_t* n_dev,
@@ -299,7 +299,7 @@ extern "C" int mfn_density_fwd(const mfn_field_cfg* cfg, const void* xyz_params_
     if (use_fused(cfg)) {
         FusedArgs f; make_fused(f, cfg, xyz_params_h, nullptr, xyzs, nullptr, n_max, n_dev);
         f.sigmas = sigmas;
-        return fused_field_forward(f, m, cfg->rgb_hidden, 2, st);
+        return fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, 2, st);
     }
     const int n_mlp1 = 64 * 32 + 16 * 64;
     const __half* p = (const __half*)xyz_params_h;

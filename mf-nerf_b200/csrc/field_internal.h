@@ -76,22 +76,22 @@ struct FusedArgs {
                              // array may already hold the next step's samples)
     __half* h_out;           // mode 3: (n, 16) fp16 raw outputs of the sigma network
     int32_t* n_out;          // training: where the forward pass leaves min(*n_dev, n_max) for the backward pass (workspace)
-    unsigned char* blobs;    // training: the saved X tile, 8 KiB per 128 samples (MFN_FIELD_SAVE=full: all five tiles, 64 KiB)
+    unsigned char* blobs;    // training: the saved X tiles, 8 KiB per 128 samples
     int rgb_act;
     // backward only
     const float* dL_dsigmas; const float* dL_drgbs; float loss_scale;
     __half* dfeats;          // level-major [16][dfeats_stride] half2, loss-scaled
     int64_t dfeats_stride;
     float4* x01;             // training: normalised positions (n,4) f32, written by the forward kernel for the scatter kernel
-    float* partials;         // [gridDim.x][10240] per-CTA weight gradients
+    float* partials;         // [gridDim.x][10240 (rgb width 64) / 25600 (128)] per-CTA weight gradients
     int32_t* overflow;
     long long* dbg;          // optional phase timestamps (tools only)
 };
 bool fused_field_supported(const mfn_field_cfg* c);
 size_t fused_blob_bytes(int64_t n_max);
-size_t fused_partial_bytes();
-int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_hidden, int mode, cudaStream_t st);   // mode 0 inference, 1 training, 2 density
+size_t fused_partial_bytes(int rgb_width);
+int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_width, int rgb_hidden, int mode, cudaStream_t st);   // mode 0 inference, 1 training, 2 density, 3 raw sigma-net outputs
 // launches the backward kernel; the reduction of its per-CTA weight-gradient partials is described in *wr for the scatter kernel to do
-int fused_field_backward(const FusedArgs& a, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, WgradReduce* wr, cudaStream_t st);
+int fused_field_backward(const FusedArgs& a, int rgb_width, int rgb_hidden, float* d_sigma_params, float* d_rgb_params, WgradReduce* wr, cudaStream_t st);
 
 }  // namespace mfn

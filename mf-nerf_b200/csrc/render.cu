@@ -256,7 +256,7 @@ extern "C" int mfn_render_iterations(const mfn_field_cfg* cfg, const void* xyz_p
                                                         cascades, grid_size, scale, exp_step_factor, max_samples, (float*)(ws + w.xyzs), (float*)(ws + w.dirs),
                                                         (float*)(ws + w.deltas), (float*)(ws + w.ts), (int32_t*)(ws + w.neff));
         note_launch(1);
-        if ((rc = fused_field_forward(f, m, cfg->rgb_hidden, 0, st)) != MFN_OK) return rc;
+        if ((rc = fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, 0, st)) != MFN_OK) return rc;
         render_composite_kernel<<<ray_blocks, 128, 0, st>>>((const float*)(ws + w.sigmas), (const float*)(ws + w.rgbs), (const float*)(ws + w.deltas),
                                                             (const float*)(ws + w.ts), (int32_t*)(ws + w.alive), list_stride, plan, T_threshold,
                                                             (const int32_t*)(ws + w.neff), opacity, depth, rgb, (int)n_rays, min_samples, max_samples,

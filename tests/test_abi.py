@@ -52,20 +52,20 @@ def test_render_and_field_entry_points_validate_arguments():
     assert b"mfn_render_begin" in lib.mfn_last_error()
     cfg = make_field_cfg(0.5)
     assert lib.mfn_render_iterations(ctypes.byref(cfg), None, None, None, None, 16, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None) == -2
-    wide = make_field_cfg(0.5, rgb_channels=128)          # 128-wide rgb net: not covered by the fused kernels -> loud error, no silent fallback
-    rc = lib.mfn_render_iterations(ctypes.byref(wide), None, None, None, None, 16, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None)
-    assert rc == -2 and b"not covered" in lib.mfn_last_error()
+    wide = make_field_cfg(0.5, rgb_channels=128)          # 128-wide rgb net (MF-NeRF's scripts): on the fused kernels since round 2
+    assert lib.mfn_field_is_fused(ctypes.byref(wide)) == 1 and lib.mfn_field_is_fused(ctypes.byref(cfg)) == 1
+    odd = make_field_cfg(0.5, rgb_channels=96)            # anything else: loud error, no silent fallback
+    assert lib.mfn_field_is_fused(ctypes.byref(odd)) == -2 and b"rgb net" in lib.mfn_last_error()
     assert lib.mfn_render_finish(None, None, None, 16, None) == -2
     assert lib.mfn_render_iterations(ctypes.byref(cfg), None, None, None, None, 0, None, 1, 0.5, 0.0, 128, 1024, 1, 1e-4, 4, None, None, None, None, 0, None) == 0   # no rays: no-op
-    assert lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1 << 20, 1) >= (1 << 20) * 512     # 64 KiB activation blob per 128 samples
+    assert lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1 << 20, 1) >= (1 << 20) * (64 + 8 + 64 + 16 + 12)   # X tile, fp16 rgb, dfeats, x01, dirs per sample
     assert lib.mfn_field_fwd(ctypes.byref(cfg), None, None, None, None, 128, None, None, None, None, 0, None) == -2
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 128, None, None, None) == -2 and b"null pointer" in lib.mfn_last_error()
-    assert lib.mfn_geo_fwd(ctypes.byref(wide), None, None, 128, None, None, None) == -2 and b"fused shape" in lib.mfn_last_error()
     assert lib.mfn_geo_fwd(ctypes.byref(cfg), None, None, 0, None, None, None) == 0
-    # MixedFeature grid: K tables of 2^T entries; runs on the unfused kernels
+    # MixedFeature grid: K tables of 2^T entries; fused like the plain hash grid
     from mfnerf_b200 import field_ops
-    mixed = make_field_cfg(0.5, log2_T=17, grid="MixedFeature", n_tables=8)
-    assert field_ops.grid_layout(mixed.grid)[0] == 8 << 17 and lib.mfn_field_is_fused(ctypes.byref(mixed)) == 0
+    mixed = make_field_cfg(0.5, log2_T=17, grid="MixedFeature", n_tables=8, rgb_channels=128)
+    assert field_ops.grid_layout(mixed.grid)[0] == 8 << 17 and lib.mfn_field_is_fused(ctypes.byref(mixed)) == 1
     assert lib.mfn_grid_layout(ctypes.byref(field_ops.make_grid_cfg(16, 2, 17, 16, 1.3, "MixedFeature", 0)), None, None, None) == -1
     with pytest.raises(NotImplementedError):
         field_ops.make_grid_cfg(16, 2, 17, 16, 1.3, "Window", 1)
@@ -106,4 +106,5 @@ def test_host_side_helpers_and_new_entry_points_validate_arguments():
     p = lib.mfn_field_count_ptr(ctypes.byref(cfg), fake, 1024)
     assert p is not None and (1 << 20) < p < (1 << 20) + lib.mfn_field_workspace_bytes(ctypes.byref(cfg), 1024, 1)
     wide = make_field_cfg(0.5, rgb_channels=128)
-    assert lib.mfn_field_count_ptr(ctypes.byref(wide), fake, 1024) is None                                                # unfused shapes keep no count
+    pw = lib.mfn_field_count_ptr(ctypes.byref(wide), fake, 1024)
+    assert pw is not None and pw > p                                                                                       # larger weight-gradient partials

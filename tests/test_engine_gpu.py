@@ -41,18 +41,21 @@ def _grad_close(got, want, name, big_frac=5e-2, rtol=8e-2, max_frac=3e-2):
     assert err.max().item() <= max_frac * sc, (name, err.max().item(), sc)
 
 
-@pytest.mark.parametrize("grid,n_tables", [("Hash", 1), ("MixedFeature", 8), ("MixedFeature", 3)])
-def test_field_fwd_bwd_vs_restatement(grid, n_tables):
+@pytest.mark.parametrize("grid,n_tables,rgb_channels,rgb_layers", [("Hash", 1, 64, 2), ("MixedFeature", 8, 64, 2), ("MixedFeature", 3, 64, 1),
+                                                                  ("Hash", 1, 128, 2), ("MixedFeature", 8, 128, 2), ("Hash", 1, 128, 1)])
+def test_field_fwd_bwd_vs_restatement(grid, n_tables, rgb_channels, rgb_layers):
     """the fused tcgen05 field kernels (mfn_field_fwd / mfn_field_bwd, what the engine's training step runs) against the torch
-    restatement, for the plain hash grid and for the fork's MixedFeature grid (--grid MixedFeature --N_tables K)"""
+    restatement: plain hash grid and the fork's MixedFeature grid (--grid MixedFeature --N_tables K), rgb net 64 or 128 wide with
+    1 or 2 hidden layers -- ("MixedFeature", 8, 128, 2) is MF-NeRF's own configuration (benchmarking/benchmark_*_mf.sh)"""
     import ctypes
     from mfnerf_b200._lib import call, ptr, stream_ptr, lib
-    eng = _engine(grid=grid, n_tables=n_tables)
+    eng = _engine(grid=grid, n_tables=n_tables, rgb_channels=rgb_channels, rgb_layers=rgb_layers)
     assert lib.mfn_field_is_fused(ctypes.byref(eng.cfg)) == 1 and eng._fused
     with torch.no_grad():
         eng.params[eng.n_mlp1:eng.n_xyz].uniform_(-0.5, 0.5)     # make the grid features matter
         eng.params_h.copy_(eng.params)
-    ref = fr.NGPRef(0.5, log2_T=15, grid=grid, n_tables=n_tables, params=(eng.params[:eng.n_xyz].cpu(), eng.params[eng.off_rgb:eng.off_rgb + eng.n_rgb].cpu())).cuda()
+    ref = fr.NGPRef(0.5, log2_T=15, grid=grid, n_tables=n_tables, rgb_channels=rgb_channels, rgb_layers=rgb_layers,
+                    params=(eng.params[:eng.n_xyz].cpu(), eng.params[eng.off_rgb:eng.off_rgb + eng.n_rgb].cpu())).cuda()
     g = torch.Generator().manual_seed(5)
     N = 3001
     x = ((torch.rand(N, 3, generator=g) - 0.5)).cuda(); d = torch.randn(N, 3, generator=g).cuda()
@@ -391,10 +394,12 @@ def test_update_density_grid_fused_kernels_follow_the_reference_rule():
 
 @pytest.mark.parametrize("rgb_channels,rgb_layers", [(128, 2), (64, 1)])
 def test_other_rgb_net_shapes(rgb_channels, rgb_layers):
-    """the MF-NeRF scripts use --rgb_channels 128 (benchmarking/benchmark_llff_nerf_mf.sh): that shape runs on the unfused mma.sync
-    pipeline (field.cu), 64 x 1 on the fused kernels' one-hidden-layer instantiation; both must train and match the restatement"""
+    """the MF-NeRF scripts use --rgb_channels 128 (benchmarking/benchmark_*_mf.sh): the 128-wide instantiation of the fused tcgen05
+    kernels (2 forward / 1 backward CTA per SM), 64 x 1 the one-hidden-layer instantiation; both must train, match the restatement
+    and render through the device-side wavefront"""
     from oracle import field_ref as fr
     eng = _engine(256, rgb_channels=rgb_channels, rgb_layers=rgb_layers)
+    assert eng._fused
     rays = scenes.scene("lego", 256, seed=12)
     o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
     tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).cuda().float()
@@ -415,6 +420,9 @@ def test_other_rgb_net_shapes(rgb_channels, rgb_layers):
         sig_r, rgb_r = ref(eng.xyzs[:n], eng.dirs[:n])
     torch.testing.assert_close(sig, sig_r, rtol=3e-2, atol=2e-3)
     torch.testing.assert_close(rgb, rgb_r, rtol=2e-2, atol=4e-3)
+    a = eng.render(o, d); b = eng.render_reference_loop(o, d)
+    assert int(a["total_samples"]) == int(b["total_samples"]) > 0
+    torch.testing.assert_close(a["rgb"], b["rgb"], rtol=0, atol=1e-6)
 
 
 def test_mixed_feature_grid_trains_and_renders():
