@@ -35,6 +35,25 @@ UNIT = "rays/s"
 WORKLOAD = "lego_synthetic_train_8192rays_scale0.5_hashL16F2T19"
 RENDER_MIN_CHUNK = 8           # lower bound of the per-iteration sample count of the test-time renderer (see engine.render)
 
+# --config: the workload.  "lego" is BASELINE.json configs[1], the one the metric is quoted on and the default; the others are the
+# remaining single-GPU-sized shapes of BASELINE.json (configs 3-5) and MF-NeRF's own script configuration, benchable on 1..8 GPUs.
+CONFIGS = {
+    "lego": dict(workload=WORKLOAD, rays=8192, engine=dict(scale=0.5, log2_T=19)),
+    # benchmarking/benchmark_synthetic_nerf_mf.sh: --batch_size 16384 --lr 2e-2 --T 20 --grid MixedFeature --N_tables 8 --rgb_channels 128 --rgb_layers 2
+    "mf_synthetic": dict(workload="lego_synthetic_train_16384rays_scale0.5_mixedfeatureK8_L16F2T20_rgb128x2", rays=16384,
+                         engine=dict(scale=0.5, log2_T=20, grid="MixedFeature", n_tables=8, rgb_channels=128, rgb_layers=2, lr=2e-2)),
+    # benchmarking/benchmark_synthetic_nerf_hash.sh: the fork's hash-grid control (T 20, 64x2 rgb net, 16384 rays)
+    "hash_synthetic": dict(workload="lego_synthetic_train_16384rays_scale0.5_hashL16F2T20", rays=16384, engine=dict(scale=0.5, log2_T=20, lr=2e-2)),
+    # BASELINE.json configs[3]: mipnerf360-shaped unbounded scene, scale 16 (6 cascades, exp_step_factor 1/256), T 2^21, distortion loss
+    "unbounded_T21": dict(workload="mipnerf360_shaped_train_8192rays_scale16_6cascades_hashL16F2T21_distortion", rays=8192,
+                          engine=dict(scale=16.0, log2_T=21, distortion_w=1e-3)),
+    # BASELINE.json configs[4]: forward-facing (LLFF) shape with distortion loss; --rays / --log2-T sweep the batch (2^13..2^20) and table (2^19..2^22)
+    "llff_distortion": dict(workload="llff_shaped_train_scale4_4cascades_hashL16F2_distortion", rays=8192, engine=dict(scale=4.0, log2_T=19, distortion_w=1e-3)),
+    # benchmarking/benchmark_mipnerf360_mf.sh shape: unbounded scene on the MixedFeature grid, T 22, 128x2 rgb net
+    "mf_unbounded_T22": dict(workload="mipnerf360_shaped_train_8192rays_scale16_mixedfeatureK8_L16F2T22_rgb128x2_distortion", rays=8192,
+                             engine=dict(scale=16.0, log2_T=22, grid="MixedFeature", n_tables=8, rgb_channels=128, rgb_layers=2, distortion_w=1e-3)),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -45,6 +64,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--config", default="lego", choices=sorted(CONFIGS), help="workload (default: BASELINE.json configs[1])")
+    ap.add_argument("--rays", type=int, default=0, help="rays per step per GPU (default: the config's)")
+    ap.add_argument("--log2-T", type=int, default=0, help="log2 of the hash-table size (default: the config's)")
     ap.add_argument("--no-python-layer", action="store_true", help="skip the gpu_reference / frozen_api legs (the reference's python layer on the GPU)")
     return ap.parse_args()
 
@@ -311,13 +333,21 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    R = R_PER_GPU
+    conf = CONFIGS[args.config]
+    ekw = dict(conf["engine"])
+    if args.log2_T:
+        ekw["log2_T"] = args.log2_T
+    R = args.rays or conf["rays"]
+    is_default = args.config == "lego" and R == R_PER_GPU and not args.log2_T
+    workload = conf["workload"] + ("" if is_default else f"_R{R}_T{ekw['log2_T']}")
     sampler = ClockSampler(local)      # NVML is initialised here, long before the timed regions (its start-up disturbs kernel launches for a while)
 
-    eng = NGPEngine(scale=0.5, n_rays=R, device=dev, world_size=world, seed=1337)
-    eng.density_grid.copy_(torch.from_numpy(syn.lego_density_grid(0.5, 1)).to(dev))
+    sample_capacity = None if R <= 16384 else R * 256      # large batches: 256 samples per ray on average instead of the worst case 1024
+    eng = NGPEngine(n_rays=R, device=dev, world_size=world, seed=1337, sample_capacity=sample_capacity, **ekw)
+    eng.density_grid.copy_(torch.from_numpy(syn.lego_density_grid(ekw["scale"], eng.cascades)).to(dev))
     eng.repack_bitfield(0.5)
-    pool_host = torch.from_numpy(make_pool(POOL, R, seed=1000 + rank)).pin_memory()
+    pool_n = max(4, min(POOL, (1 << 23) // R))     # distinct ray batches cycled through (64 at the default batch size)
+    pool_host = torch.from_numpy(make_pool(pool_n, R, seed=1000 + rank)).pin_memory()
     pool_dev = pool_host.to(dev)
     loss_host = torch.zeros(K + W + 8, 3).pin_memory()
     torch.cuda.synchronize(dev)
@@ -327,7 +357,7 @@ def run_ours(args):
 
     def step_from(pool, i_host_loss=None):
         s = state["step"]
-        eng.train_step_packed(pool[s % POOL], global_step=s)
+        eng.train_step_packed(pool[s % pool_n], global_step=s)
         if i_host_loss is not None:
             eng.loss_to_host(loss_host[i_host_loss])
         state["step"] = s + 1
@@ -497,14 +527,14 @@ def run_ours(args):
 
     # ---- the reference's python layer on the same GPU, same batches (rank 0 of a 1-GPU run only): GPU-ref A+B and the frozen API
     gpu_ref = frozen = None
-    if rank == 0 and world == 1 and not args.no_python_layer:
+    if rank == 0 and world == 1 and not args.no_python_layer and is_default:
         eng.flush(); torch.cuda.synchronize(dev)
         n_ref, w_ref = min(K, 64), min(W, 64)
         gpu_ref = python_layer_arm("gpu_reference", dev, pool_dev, n_ref, w_ref)
         frozen = python_layer_arm("frozen_api", dev, pool_dev, n_ref, w_ref)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and is_default:
         v, info = cpu_reference(12, W)
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"], "samples_per_ray": info["samples_per_ray"],
                "same_schedule_as_gpu_arm": info["same_schedule"]}
@@ -513,11 +543,12 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": R, "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of fp32 grads" if world > 1 else ""),
+            "config": {"workload": workload, "name": args.config, "engine": {k: v for k, v in ekw.items()}, "n_params": int(eng.n_params),
+                       "rays_per_step_per_gpu": R, "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of fp32 grads" if world > 1 else ""),
                        "density_grid_update_every": 16, "optimizer": "fused Adam eps=1e-15 inside the timed region", "cuda_graph": not args.no_graph,
                        "extra_untimed_warmup_steps": extra_warmup,
-                       "l2": "per-step working set (fp32 params+grads+Adam moments 183 MB, fp16 table 23 MB, sample arrays) exceeds the 126 MB L2; "
-                             f"{POOL} distinct ray batches are cycled",
+                       "l2": f"per-step working set (fp32 params+grads+Adam moments {16 * eng.n_params / 1e6:.0f} MB, fp16 table {2 * eng.n_params / 1e6:.0f} MB, sample "
+                             f"arrays) exceeds the 126 MB L2; {pool_n} distinct ray batches are cycled",
                        "mixed_precision": "fp16 table/weights/activations, fp32 accumulation, fp32 master params (reference: AMP precision=16)"},
             "samples_per_sec": samples_dev / (ms_dev * 1e-3), "samples_per_ray": samples_dev / rays_total,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(3 * R * 3 * 4), "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K,

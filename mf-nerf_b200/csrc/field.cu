@@ -144,6 +144,10 @@ static inline unsigned ew_grid(int64_t n_max) {
 
 using namespace mfn;
 
+static size_t ws_need(const mfn_field_cfg* cfg, int64_t n_max, bool training) {
+    return use_fused(cfg) ? fused_ws(cfg, n_max, training).total : field_ws(cfg, n_max, training).total;
+}
+
 extern "C" int mfn_field_is_fused(const mfn_field_cfg* cfg) {
     if (field_cfg_ok(cfg, "mfn_field_is_fused") != MFN_OK) return MFN_ERR_ARG;
     return use_fused(cfg) ? 1 : 0;
@@ -156,9 +160,8 @@ extern "C" void* mfn_field_count_ptr(const mfn_field_cfg* cfg, void* workspace, 
 
 extern "C" int64_t mfn_field_workspace_bytes(const mfn_field_cfg* cfg, int64_t n_max, int training) {
     if (field_cfg_ok(cfg, "mfn_field_workspace_bytes") != MFN_OK || n_max < 0) return -1;
-    const size_t v1 = field_ws(cfg, n_max, training != 0).total;
-    const size_t fz = fused_field_supported(cfg) ? fused_ws(cfg, n_max, training != 0).total : 0;
-    return (int64_t)(v1 > fz ? v1 : fz);
+    // the fused kernels keep ~170 B/sample in training and nothing at inference; the v1 pipeline (MFN_FIELD_IMPL=v1) every intermediate
+    return (int64_t)ws_need(cfg, n_max, training != 0);
 }
 
 static void make_enc(EncArgs& e, const mfn_field_cfg* cfg, const float* xyzs, int64_t n_max, const int32_t* n_dev) {
@@ -185,7 +188,7 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     if (n_max < 0) { set_error("mfn_field_fwd: bad n_max"); return MFN_ERR_ARG; }
     if (n_max == 0) return MFN_OK;
     const FieldWs w = field_ws(cfg, n_max, false);
-    if (!xyz_params_h || !rgb_params_h || !xyzs || !dirs || !sigmas || !rgbs || !workspace || (size_t)workspace_bytes < w.total) {
+    if (!xyz_params_h || !rgb_params_h || !xyzs || !dirs || !sigmas || !rgbs || !workspace || (size_t)workspace_bytes < ws_need(cfg, n_max, false)) {
         set_error("mfn_field_fwd: null pointer or workspace too small"); return MFN_ERR_ARG;
     }
     GridMeta m;
@@ -228,7 +231,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     if (n_max == 0) return MFN_OK;
     const FieldWs w = field_ws(cfg, n_max, true);
     if (!xyz_params_h || !rgb_params_h || !xyzs || !dL_dsigmas || !dL_drgbs || !d_xyz_params || !d_rgb_params || !workspace ||
-        (size_t)workspace_bytes < w.total) { set_error("mfn_field_bwd: null pointer or workspace too small"); return MFN_ERR_ARG; }
+        (size_t)workspace_bytes < ws_need(cfg, n_max, true)) { set_error("mfn_field_bwd: null pointer or workspace too small"); return MFN_ERR_ARG; }
     GridMeta m;
     if ((rc = build_grid_meta(&cfg->grid, &m, "mfn_field_bwd")) != MFN_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -289,7 +292,7 @@ extern "C" int mfn_density_fwd(const mfn_field_cfg* cfg, const void* xyz_params_
     if (n_max < 0) { set_error("mfn_density_fwd: bad n_max"); return MFN_ERR_ARG; }
     if (n_max == 0) return MFN_OK;
     const FieldWs w = field_ws(cfg, n_max, false);
-    if (!xyz_params_h || !xyzs || !sigmas || !workspace || (size_t)workspace_bytes < w.total) {
+    if (!xyz_params_h || !xyzs || !sigmas || !workspace || (size_t)workspace_bytes < ws_need(cfg, n_max, false)) {
         set_error("mfn_density_fwd: null pointer or workspace too small"); return MFN_ERR_ARG;
     }
     GridMeta m;

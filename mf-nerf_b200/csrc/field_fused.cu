@@ -474,6 +474,18 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     uint32_t ph_mma = 0, ph_load0 = 0, ph_load1 = 0;
     uint32_t acc = 0;                                              // 0 on the CTA's first tile: weight-gradient MMAs overwrite
     bool bad = false;
+    // per-row inputs of a tile, requested one tile ahead (their latency used to open every tile: ~1.5 k of its ~12 k cycles):
+    // thread 0 of a row: fp16 rgb outputs + dL/drgb; its partner: the view direction
+    float pf[3] = {0.f, 0.f, 0.f};
+    uint2 pfy = make_uint2(0u, 0u);
+    auto prefetch_row = [&](int64_t t) {
+        const int64_t ip = t * kFT + row;
+        if (ip < n) {
+            if (hsel == 0) { pfy = a.rgb_h[ip]; pf[0] = a.dL_drgbs[3 * ip]; pf[1] = a.dL_drgbs[3 * ip + 1]; pf[2] = a.dL_drgbs[3 * ip + 2]; }
+            else { pf[0] = a.dirs_copy[3 * ip]; pf[1] = a.dirs_copy[3 * ip + 1]; pf[2] = a.dirs_copy[3 * ip + 2]; }
+        }
+    };
+    if ((int64_t)blockIdx.x < n_tiles) prefetch_row(blockIdx.x);
 
     int tile_no = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
@@ -489,16 +501,17 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             bulk_g2s_hint(smem + L::BX + (xbuf ^ 1) * kBlobX, a.blobs + (size_t)(tile + gridDim.x) * kBlobX, kBlobX, &bar_load[xbuf ^ 1], pol_stream);
         }
         // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
+        const float dsig = valid ? a.dL_dsigmas[i] : 0.f;        // used in stage C: in flight until then
         if (hsel == 0) {
             float g[3] = {0.f, 0.f, 0.f};
             if (valid) {
-                const uint2 yh = a.rgb_h[i];
+                const uint2 yh = pfy;
                 const float2 y01 = __half22float2(*reinterpret_cast<const __half2*>(&yh.x));
                 const float y3[3] = {y01.x, y01.y, __low2float(*reinterpret_cast<const __half2*>(&yh.y))};
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float yv = y3[k];
-                    float d = a.dL_drgbs[3 * i + k] * a.loss_scale;
+                    float d = pf[k] * a.loss_scale;
                     if (a.rgb_act == MFN_ACT_SIGMOID) d *= yv * (1.f - yv);
                     else if (a.rgb_act == MFN_ACT_EXP) d *= yv;
                     g[k] = d;
@@ -511,7 +524,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             *reinterpret_cast<uint4*>(smem + L::BDZo + tile_off(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
         } else {   // the partner thread re-encodes the view direction: CAT[:, 0:16] (same code, same bits as the forward pass)
             uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
-            if (valid) sh_of_dir(a.dirs_copy[3 * i], a.dirs_copy[3 * i + 1], a.dirs_copy[3 * i + 2], o0, o1);
+            if (valid) sh_of_dir(pf[0], pf[1], pf[2], o0, o1);
             *reinterpret_cast<uint4*>(smem + L::BC + tile_off(row, 0, 32)) = o0;
             *reinterpret_cast<uint4*>(smem + L::BC + tile_off(row, 8, 32)) = o1;
         }
@@ -569,6 +582,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         MFN_MMA_WAIT();
         mask_epilogue<RW>(trow + L::AccH, pHL, row, hsel);                  // dZ of the last hidden layer, in place
+        if (tile + gridDim.x < n_tiles) prefetch_row(tile + gridDim.x);
         MFN_STAGE_SYNC();
         if (NH2 == 2) {
             // ---- stage B: dH2 = dZ4 . W4 ;  dW4^T += H2^T . dZ4
@@ -597,7 +611,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             float d0 = __uint_as_float(r[0]);
             if (valid) {
                 const float h0 = __half2float(*reinterpret_cast<const __half*>(smem + L::BC + tile_off(row, 16, 32)));
-                d0 += a.dL_dsigmas[i] * expf(fminf(fmaxf(h0, -15.f), 15.f)) * a.loss_scale;
+                d0 += dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) * a.loss_scale;
             }
             r[0] = __float_as_uint(d0);
             uint4 o0, o1;

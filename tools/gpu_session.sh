@@ -1,20 +1,19 @@
 #!/bin/bash
-# one gpurun call: full GPU suite (no -x, every failure listed) + default bench
 mkdir -p gpurun_out
-T=${1:-s4}
+T=${1:-s5}
 timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 -W ignore::FutureWarning > gpurun_out/${T}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 900 python bench.py > gpurun_out/${T}_bench.log 2> gpurun_out/${T}_bench.err
+timeout 900 python bench.py --no-python-layer --no-cpu-baseline > gpurun_out/${T}_bench.log 2> gpurun_out/${T}_bench.err
 echo "bench rc=$?" >> gpurun_out/${T}_bench.err
-grep -E "passed|failed|FAILED" gpurun_out/${T}_pytest.log | tail -8
+timeout 300 python tools/fwd_phases.py > gpurun_out/${T}_phases.log 2>&1
+grep -E "passed|failed|FAILED" gpurun_out/${T}_pytest.log | tail -12
 python - <<PY
 import json
 for f in ("bench",):
     try:
         d=json.loads(open(f"gpurun_out/${T}_{f}.log").read().strip().splitlines()[-1])
-        print(f, round(d["value"]/1e6,2),"Mrays/s", round(d["ms_per_step"],4),"ms", round(d["samples_per_sec"]/1e6),"Msamp/s", d["kernel_us"])
-        for k in ("gpu_reference","frozen_api","cpu_baseline","l2_roofline","roofline"): print(k, d.get(k))
+        print(f, round(d["value"]/1e6,2),"Mrays/s", round(d["ms_per_step"],4),"ms", round(d["samples_per_sec"]/1e6),"Msamp/s", d["kernel_us"], d["render"]["fps_800x800"])
     except Exception as e:
         print(f, "ERR", e)
 PY
-tail -3 gpurun_out/${T}_bench.err
+tail -3 gpurun_out/${T}_bench.err; tail -8 gpurun_out/${T}_phases.log
