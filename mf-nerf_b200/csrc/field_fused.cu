@@ -287,6 +287,10 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         tc_fence_before();
         __syncthreads();
         MFN_TS(2);
+        // the view direction of this row (partner thread), requested now so that the layer-1 MMA wait hides its latency: a load issued
+        // just before a stage boundary is waited for by the boundary's proxy fence
+        float dirx = 0.f, diry = 0.f, dirz = 1.f;
+        if (RGB && hsel == 1 && valid) { dirx = a.dirs[3 * i]; diry = a.dirs[3 * i + 1]; dirz = a.dirs[3 * i + 2]; }
         // ---- layer 1: H1 = relu(X . W1^T)
         if (tid == 0) {
             tc_fence_after();
@@ -330,9 +334,8 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             mbar_wait(&bar, phase);
             uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
             if (valid) {
-                const float dx = a.dirs[3 * i], dy = a.dirs[3 * i + 1], dz = a.dirs[3 * i + 2];
-                if (TRAIN) { a.dirs_copy[3 * i] = dx; a.dirs_copy[3 * i + 1] = dy; a.dirs_copy[3 * i + 2] = dz; }   // the backward pass re-encodes it
-                sh_of_dir(dx, dy, dz, o0, o1);
+                if (TRAIN) { a.dirs_copy[3 * i] = dirx; a.dirs_copy[3 * i + 1] = diry; a.dirs_copy[3 * i + 2] = dirz; }   // the backward pass re-encodes it
+                sh_of_dir(dirx, diry, dirz, o0, o1);
             }
             *reinterpret_cast<uint4*>(smem + oT + tile_off(row, 0, 32)) = o0;
             *reinterpret_cast<uint4*>(smem + oT + tile_off(row, 8, 32)) = o1;
@@ -405,7 +408,10 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------------ backward
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 288;        // 8 epilogue warps (two threads per sample row) + 1 warp whose lane 0 issues every MMA and bulk copy:
+                                        // its issue path never has a global load of its own outstanding (measured: the stage that followed the
+                                        // per-row prefetch waited ~1.5 k cycles when the issuing thread was also a row thread)
+constexpr int kBwdIssuer = 256;
 
 // TMEM (fp32 dgrad accumulator) -> mask with relu'(activation tile row) -> fp16 dZ row written IN PLACE of the activation row
 template <int C>
@@ -435,7 +441,7 @@ __device__ __forceinline__ void mask_epilogue(uint32_t taddr, unsigned char* til
 }
 
 // phase timestamps of CTA 0 / thread 0 of the backward kernel (tools/fwd_phases.py): after every MMA-completion wait and every barrier
-#define MFN_BTS() do { if (a.dbg && blockIdx.x == 0 && tid == 0 && tile_no < 6 && ts_k < 40) a.dbg[256 + tile_no * 40 + (ts_k++)] = clock64(); } while (0)
+#define MFN_BTS() do { if (a.dbg && blockIdx.x == 0 && tid == kBwdIssuer && tile_no < 6 && ts_k < 40) a.dbg[256 + tile_no * 40 + (ts_k++)] = clock64(); } while (0)
 // one stage boundary: generic-proxy writes of the tiles -> async proxy (MMA), TMEM reads done, CTA barrier
 #define MFN_STAGE_SYNC() do { fence_async_smem(); tc_fence_before(); __syncthreads(); MFN_BTS(); } while (0)
 #define MFN_MMA_WAIT() do { mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1u; MFN_BTS(); tc_fence_after(); } while (0)
@@ -448,11 +454,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     __shared__ uint64_t bar_mma, bar_load[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = tid & (kFT - 1), hsel = tid >> 7;   // two threads per sample row: they split the accumulator columns
+    const int row = tid & (kFT - 1), hsel = tid >> 7;   // two threads per sample row: they split the accumulator columns (hsel == 2: issuer warp)
+    const bool worker = tid < 256, issuer = tid == kBwdIssuer;
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
     const uint64_t pol_stream = policy_evict_first();
-    if (tid == 0) {
+    if (issuer) {
         mbar_init(&bar_mma, 1); mbar_init(&bar_load[0], 1); mbar_init(&bar_load[1], 1); mbar_fence_init();
         if ((int64_t)blockIdx.x < n_tiles) {      // first X tile: in flight while the weights are staged
             mbar_arrive_expect_tx(&bar_load[0], kBlobX);
@@ -485,23 +492,22 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             else { pf[0] = a.dirs_copy[3 * ip]; pf[1] = a.dirs_copy[3 * ip + 1]; pf[2] = a.dirs_copy[3 * ip + 2]; }
         }
     };
-    if ((int64_t)blockIdx.x < n_tiles) prefetch_row(blockIdx.x);
+    if (worker && (int64_t)blockIdx.x < n_tiles) prefetch_row(blockIdx.x);
 
     int tile_no = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
         int ts_k = 0;
         MFN_BTS();
         const int64_t i = tile * kFT + row;
-        const bool valid = i < n;
+        const bool valid = worker && i < n;
         const int xbuf = tile_no & 1;
         const uint32_t sX = sbase + L::BX + xbuf * kBlobX;
-        if (tid == 0 && tile + gridDim.x < n_tiles) {   // prefetch the NEXT tile's X into the other buffer (its last reader, stage E of the
+        if (issuer && tile + gridDim.x < n_tiles) {   // prefetch the NEXT tile's X into the other buffer (its last reader, stage E of the
                                                          // previous tile, finished before the barrier that ended that tile)
             mbar_arrive_expect_tx(&bar_load[xbuf ^ 1], kBlobX);
             bulk_g2s_hint(smem + L::BX + (xbuf ^ 1) * kBlobX, a.blobs + (size_t)(tile + gridDim.x) * kBlobX, kBlobX, &bar_load[xbuf ^ 1], pol_stream);
         }
         // ---- dZ5 = loss_scale * dL/drgb * act'(rgb)   (16 columns, 3 live)
-        const float dsig = valid ? a.dL_dsigmas[i] : 0.f;        // used in stage C: in flight until then
         if (hsel == 0) {
             float g[3] = {0.f, 0.f, 0.f};
             if (valid) {
@@ -522,7 +528,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             bad |= !isfinite(__low2float(hh[0])) || !isfinite(__high2float(hh[0])) || !isfinite(__low2float(hh[1]));
             *reinterpret_cast<uint4*>(smem + L::BDZo + tile_off(row, 0, 16)) = o0;
             *reinterpret_cast<uint4*>(smem + L::BDZo + tile_off(row, 8, 16)) = make_uint4(0u, 0u, 0u, 0u);
-        } else {   // the partner thread re-encodes the view direction: CAT[:, 0:16] (same code, same bits as the forward pass)
+        } else if (hsel == 1) {   // the partner thread re-encodes the view direction: CAT[:, 0:16] (same code, same bits as the forward pass)
             uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0;
             if (valid) sh_of_dir(pf[0], pf[1], pf[2], o0, o1);
             *reinterpret_cast<uint4*>(smem + L::BC + tile_off(row, 0, 32)) = o0;
@@ -530,16 +536,17 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         if (xbuf == 0) { mbar_wait(&bar_load[0], ph_load0); ph_load0 ^= 1u; } else { mbar_wait(&bar_load[1], ph_load1); ph_load1 ^= 1u; }
         MFN_STAGE_SYNC();
+        const float dsig = (valid && hsel == 0) ? a.dL_dsigmas[i] : 0.f;        // used in stage C; requested after the boundary (see below)
         // ---- recomputed forward: H1 = relu(X.W1^T) ; h = H1.W2^T -> CAT[:, 16:32] ; H2 = relu(CAT.W3^T) ; H3 = relu(H2.W4^T)
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sX, 32, 0), kstep_kmajor(), desc_kmajor(sbase + L::W1, 32, 0), kstep_kmajor(), idesc_f16(128, 64, false, false), 2, 0u);
             mma_commit(&bar_mma);
         }
         MFN_MMA_WAIT();
-        relu_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel);
+        if (worker) relu_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel);
         MFN_STAGE_SYNC();
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccO2, desc_kmajor(sH1, 64, 0), kstep_kmajor(), desc_kmajor(sbase + L::W2, 64, 0), kstep_kmajor(), idesc_f16(128, 16, false, false), 4, 0u);
             mma_commit(&bar_mma);
@@ -555,49 +562,51 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             *reinterpret_cast<uint4*>(smem + L::BC + tile_off(row, 24, 32)) = o1;
         }
         MFN_STAGE_SYNC();
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sC, 32, 0), kstep_kmajor(), desc_kmajor(sbase + L::W3, 32, 0), kstep_kmajor(), idesc_f16(128, RW, false, false), 2, 0u);
             mma_commit(&bar_mma);
         }
         MFN_MMA_WAIT();
-        relu_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel);
+        if (worker) relu_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel);
         MFN_STAGE_SYNC();
         if (NH2 == 2) {
-            if (tid == 0) {
+            if (issuer) {
                 tc_fence_after();
                 mma_chain(tbase + L::AccH, desc_kmajor(sH2, RW, 0), kstep_kmajor(), desc_kmajor(sbase + L::W4, RW, 0), kstep_kmajor(), idesc_f16(128, RW, false, false), RW / 16, 0u);
                 mma_commit(&bar_mma);
             }
             MFN_MMA_WAIT();
-            relu_epilogue<RW>(trow + L::AccH, smem + L::BH3, row, hsel);
+            if (worker) relu_epilogue<RW>(trow + L::AccH, smem + L::BH3, row, hsel);
             MFN_STAGE_SYNC();
         }
         // ---- stage A: dH_last = dZ5 . W5 ;  dW5^T += H_last^T . dZ5
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_f16_ss(tbase + L::AccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + L::W5, RW, 0), idesc_f16(128, RW, false, true), 0u);
             mma_chain(tbase + L::AccW5, desc_mnmajor(sHL, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(RW, 16, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
         }
         MFN_MMA_WAIT();
-        mask_epilogue<RW>(trow + L::AccH, pHL, row, hsel);                  // dZ of the last hidden layer, in place
-        if (tile + gridDim.x < n_tiles) prefetch_row(tile + gridDim.x);
+        if (worker) mask_epilogue<RW>(trow + L::AccH, pHL, row, hsel);                  // dZ of the last hidden layer, in place
         MFN_STAGE_SYNC();
+        // next tile's per-row inputs: requested right AFTER a stage boundary -- the proxy fence of a boundary waits for the thread's
+        // outstanding global loads (measured: +1.5 k cycles when they were issued just before one), the MMA wait that follows hides them
+        if (worker && tile + gridDim.x < n_tiles) prefetch_row(tile + gridDim.x);
         if (NH2 == 2) {
             // ---- stage B: dH2 = dZ4 . W4 ;  dW4^T += H2^T . dZ4
-            if (tid == 0) {
+            if (issuer) {
                 tc_fence_after();
                 mma_chain(tbase + L::AccH, desc_kmajor(sH3, RW, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W4, RW, 0), kstep_mnmajor(RW), idesc_f16(128, RW, false, true), RW / 16, 0u);
                 mma_chain(tbase + L::AccW4, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sH3, RW, 0), kstep_mnmajor(RW), idesc_f16(RW, RW, true, true), kFT / 16, acc);
                 mma_commit(&bar_mma);
             }
             MFN_MMA_WAIT();
-            mask_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel);    // dZ3 in place of H2
+            if (worker) mask_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel);    // dZ3 in place of H2
             MFN_STAGE_SYNC();
         }
         // ---- stage C: dCAT = dZ3 . W3 (32 columns) ;  dW3 += dZ3^T . CAT
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sH2, RW, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W3, 32, 0), kstep_mnmajor(32), idesc_f16(128, 32, false, true), RW / 16, 0u);
             mma_chain(tbase + L::AccW3, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sC, 32, 0), kstep_mnmajor(32), idesc_f16(RW, 32, true, true), kFT / 16, acc);
@@ -622,24 +631,24 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         }
         MFN_STAGE_SYNC();
         // ---- stage D: dH1 = dZ2 . W2 ;  dW2^T += H1^T . dZ2
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_f16_ss(tbase + L::AccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + L::W2, 64, 0), idesc_f16(128, 64, false, true), 0u);
             mma_chain(tbase + L::AccW2, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(64, 16, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
         }
         MFN_MMA_WAIT();
-        mask_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel);        // dZ1 in place of H1
+        if (worker) mask_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel);        // dZ1 in place of H1
         MFN_STAGE_SYNC();
         // ---- stage E: dX = dZ1 . W1 (32 columns) ;  dW1 += dZ1^T . X
-        if (tid == 0) {
+        if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sH1, 64, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W1, 32, 0), kstep_mnmajor(32), idesc_f16(128, 32, false, true), 4, 0u);
             mma_chain(tbase + L::AccW1, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sX, 32, 0), kstep_mnmajor(32), idesc_f16(64, 32, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
         }
         MFN_MMA_WAIT();
-        {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel; each thread of a row does 8 levels
+        if (worker) {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel; each thread of a row does 8 levels
             uint32_t r[16];
             tmem_ld_x16(trow + L::AccH + 16 * hsel, r);
             tmem_ld_wait();

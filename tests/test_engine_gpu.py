@@ -32,13 +32,7 @@ def _engine(n_rays=512, T=15, **kw):
     return eng
 
 
-def _grad_close(got, want, name, big_frac=5e-2, rtol=8e-2, max_frac=3e-2):
-    sc = want.abs().max().item()
-    err = (got - want).abs()
-    big = want.abs() > big_frac * sc
-    assert big.sum() > 20, name
-    assert (err[big] <= rtol * want.abs()[big] + 2e-3 * sc).all(), (name, err[big].max().item(), sc)
-    assert err.max().item() <= max_frac * sc, (name, err.max().item(), sc)
+from parity import grad_close as _grad_close  # noqa: E402
 
 
 @pytest.mark.parametrize("grid,n_tables,rgb_channels,rgb_layers", [("Hash", 1, 64, 2), ("MixedFeature", 8, 64, 2), ("MixedFeature", 3, 64, 1),

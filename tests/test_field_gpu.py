@@ -11,6 +11,8 @@ import torch
 
 from oracle import field_ref as fr
 
+from parity import grad_close  # noqa: E402
+
 pytestmark = pytest.mark.gpu
 
 
@@ -91,11 +93,7 @@ def test_mlp_forward_backward(in_dim, width, n_hidden, act, N):
     dx = ops.mlp_bwd(dy, xd, acts, out, wd, in_dim, width, n_hidden, act, dW)
     (want * dy.float()).sum().backward()
     for got, ref, name in ((dx.float(), x32.grad, "dx"), (dW, w32.grad, "dW")):
-        scale = ref.abs().max().item()
-        err = (got - ref).abs()
-        big = ref.abs() > 2e-2 * scale
-        assert (err[big] <= 5e-2 * ref.abs()[big] + 1e-3 * scale).all(), (name, err.max().item(), scale)
-        assert err.max().item() <= 2e-2 * scale, (name, err.max().item(), scale)
+        grad_close(got, ref, name, big_frac=2e-2, rtol=5e-2, atol_frac=1e-3, max_frac=2e-2)
     # accumulate semantics: a second backward doubles dW
     ops.mlp_bwd(dy, xd, acts, out, wd, in_dim, width, n_hidden, act, dW, need_dx=False)
     torch.testing.assert_close(dW, 2 * w32.grad, rtol=5e-2, atol=2e-2 * w32.grad.abs().max().item())
@@ -153,12 +151,7 @@ def test_tcnn_dropin_modules_match_ngp_restatement():
     ((sig * gs).sum() + (rgbs.float() * gc).sum()).backward()
     ((sig_r * gs).sum() + (rgbs_r * gc).sum()).backward()
     for got, want, name in ((xyz_encoder.params.grad, ref.xyz_params.grad, "xyz"), (rgb_net.params.grad, ref.rgb_params.grad, "rgb")):
-        sc = want.abs().max().item()
-        err = (got - want).abs()
-        big = want.abs() > 5e-2 * sc
-        assert big.sum() > 50
-        assert (err[big] <= 8e-2 * want.abs()[big] + 2e-3 * sc).all(), (name, err[big].max().item(), sc)
-        assert err.max().item() <= 3e-2 * sc, (name, err.max().item(), sc)
+        grad_close(got, want, name, min_big=50)
 
 
 def test_input_gradients_for_optimize_ext():
@@ -302,10 +295,7 @@ def test_tcnn_dropin_mixed_feature_grid():
     (h.float() * gout).sum().backward()
     (want * gout).sum().backward()
     got, ref = enc.params.grad, p.grad
-    sc = ref.abs().max().item()
-    big = ref.abs() > 5e-2 * sc
-    assert big.sum() > 50 and (got - ref).abs().max().item() <= 3e-2 * sc
-    assert ((got - ref).abs()[big] <= 8e-2 * ref.abs()[big] + 2e-3 * sc).all()
+    grad_close(got, ref, "mixed-feature params", min_big=50)
     with pytest.raises(NotImplementedError):
         tcnn.Encoding(3, {"otype": "WindowGrid", "type": "Window", "n_levels": 16, "n_features_per_level": 2, "log2_hashmap_size": 15,
                           "base_resolution": 16, "n_tables": 1, "per_level_scale": b})

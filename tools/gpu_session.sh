@@ -17,3 +17,5 @@ for f in ("bench",):
         print(f, "ERR", e)
 PY
 tail -3 gpurun_out/${T}_bench.err; tail -8 gpurun_out/${T}_phases.log
+timeout 300 python tools/bwd_check.py > gpurun_out/${T}_bwdcheck.log 2>&1; MFN_FIELD_IMPL=v1 timeout 300 python tools/bwd_check.py > gpurun_out/${T}_bwdcheck_v1.log 2>&1
+cat gpurun_out/${T}_bwdcheck.log gpurun_out/${T}_bwdcheck_v1.log | cut -c1-220
