@@ -425,6 +425,7 @@ def run_ours(args):
             timed(pool_dev, False)
     ms_dev, launches, samples_dev = timed(pool_dev, False)
     clocks = sampler.stop()
+    amp = eng.amp_state()                # loss scale and the number of steps skipped for fp16 overflow since the engine was built
     # ---- end-to-end run: rays + targets from pinned host memory every step, loss read back every step
     if not os.environ.get("MFN_BENCH_SWAP"):
         ms_e2e, _, _ = timed(pool_host, True)
@@ -554,7 +555,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(3 * R * 3 * 4), "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / K,
                     "api": "NGPEngine.train_step_packed(host_pinned_batch) -> C ABI; loss copied to pinned host memory every step"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "l2_roofline": l2_roofline, "kernel_us": breakdown, "cpu_baseline": cpu, "gpu_reference": gpu_ref, "frozen_api": frozen, "render": render,
-            "final_loss_terms": final_loss,
+            "final_loss_terms": final_loss, "amp": amp,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -304,6 +304,21 @@ int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
 /* the same step with its per-step scalars in DEVICE memory, hyper_dev = {lr, 1 - beta1^step, 1 - beta2^step} (fill a host copy with
  * mfn_adam_hyper and upload it ahead of time): nothing in the launch changes from step to step, so it can be part of a CUDA graph. */
 int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host);
+/* ---- AMP bookkeeping (the reference trains under Lightning precision=16: autocast + torch.amp.GradScaler, train.py:284-295) -------
+ * amp_state = 4 floats in DEVICE memory {loss scale, growth tracker, skipped steps (total), applied steps (total)}; the caller
+ * initialises it to {scale0, 0, 0, 0}.  mfn_field_bwd_amp scales the gradients by amp_state[0]; mfn_adam_step_amp unscales by
+ * inv_world / amp_state[0] (inv_world = 1 / number of data-parallel ranks whose gradients were summed), takes lr from lr_dev[0] and
+ * the bias corrections from amp_state[3] + 1 -- a skipped step does not advance Adam's t; mfn_amp_update then applies GradScaler's
+ * update rule from the overflow flag (skip -> scale *= backoff; `growth_interval` consecutive applied steps -> scale *= growth).
+ * Nothing in these launches changes from step to step, so all three can sit in a CUDA graph. */
+int mfn_field_bwd_amp(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
+                      const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, const float* amp_state, float* d_xyz_params,
+                      float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+int mfn_adam_step_amp(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* lr_dev,
+                      float beta1, float beta2, float eps, float inv_world, const float* amp_state, const int32_t* skip_flag, int zero_grad,
+                      void* stream);
+int mfn_amp_update(float* amp_state, const int32_t* skip_flag, float backoff, float growth, int growth_interval, float min_scale,
+                   float max_scale, void* stream);
 int mfn_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* hyper_dev,
                       float beta1, float beta2, float eps, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
 int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);

@@ -222,9 +222,31 @@ extern "C" int mfn_field_fwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
     return check_launch("mfn_field_fwd", st);
 }
 
+static int field_bwd_impl(const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
+                          const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale, const float* loss_scale_dev,
+                          float* d_xyz_params, float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream);
+
 extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
                              const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale, float* d_xyz_params,
                              float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream) {
+    return field_bwd_impl(cfg, xyz_params_h, rgb_params_h, xyzs, n_max, n_dev, dL_dsigmas, dL_drgbs, loss_scale, nullptr, d_xyz_params, d_rgb_params,
+                          overflow_flag, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mfn_field_bwd_amp(const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
+                                 const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, const float* amp_state, float* d_xyz_params,
+                                 float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!amp_state) { set_error("mfn_field_bwd_amp: null pointer"); return MFN_ERR_ARG; }
+    if (field_cfg_ok(cfg, "mfn_field_bwd_amp") == MFN_OK && !use_fused(cfg)) {
+        set_error("mfn_field_bwd_amp: the device-side loss scale is read by the fused kernels only (MFN_FIELD_IMPL=v1 takes mfn_field_bwd)"); return MFN_ERR_ARG;
+    }
+    return field_bwd_impl(cfg, xyz_params_h, rgb_params_h, xyzs, n_max, n_dev, dL_dsigmas, dL_drgbs, 0.f, amp_state, d_xyz_params, d_rgb_params,
+                          overflow_flag, workspace, workspace_bytes, stream);
+}
+
+static int field_bwd_impl(const mfn_field_cfg* cfg, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
+                          const int32_t* n_dev, const float* dL_dsigmas, const float* dL_drgbs, float loss_scale, const float* loss_scale_dev,
+                          float* d_xyz_params, float* d_rgb_params, int32_t* overflow_flag, void* workspace, int64_t workspace_bytes, void* stream) {
     int rc = field_cfg_ok(cfg, "mfn_field_bwd");
     if (rc != MFN_OK) return rc;
     if (n_max < 0) { set_error("mfn_field_bwd: bad n_max"); return MFN_ERR_ARG; }
@@ -242,7 +264,7 @@ extern "C" int mfn_field_bwd(const mfn_field_cfg* cfg, const void* xyz_params_h,
         FusedArgs f; make_fused(f, cfg, xyz_params_h, rgb_params_h, xyzs, nullptr, n_max, n_dev);
         f.blobs = (unsigned char*)ws + fw.blobs; f.rgb_h = (uint2*)(ws + fw.rgb); f.dirs_copy = (float*)(ws + fw.dirs); f.dfeats = (__half*)(ws + fw.dfeats);
         f.dfeats_stride = (n_max + 63) / 64 * 64;
-        f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.overflow = overflow_flag;
+        f.partials = (float*)(ws + fw.partials); f.dL_dsigmas = dL_dsigmas; f.dL_drgbs = dL_drgbs; f.loss_scale = loss_scale; f.loss_scale_dev = loss_scale_dev; f.overflow = overflow_flag;
         { static const char* dbg_env = getenv("MFN_FWD_DBG"); if (dbg_env) f.dbg = (long long*)strtoull(dbg_env, nullptr, 0); }
         WgradReduce wr{};
         if ((rc = fused_field_backward(f, cfg->rgb_width, cfg->rgb_hidden, d_xyz_params, d_rgb_params, &wr, st)) != MFN_OK) return rc;

@@ -459,6 +459,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
     const uint64_t pol_stream = policy_evict_first();
+    const float loss_scale = a.loss_scale_dev ? *a.loss_scale_dev : a.loss_scale;
     if (issuer) {
         mbar_init(&bar_mma, 1); mbar_init(&bar_load[0], 1); mbar_init(&bar_load[1], 1); mbar_fence_init();
         if ((int64_t)blockIdx.x < n_tiles) {      // first X tile: in flight while the weights are staged
@@ -517,7 +518,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const float yv = y3[k];
-                    float d = pf[k] * a.loss_scale;
+                    float d = pf[k] * loss_scale;
                     if (a.rgb_act == MFN_ACT_SIGMOID) d *= yv * (1.f - yv);
                     else if (a.rgb_act == MFN_ACT_EXP) d *= yv;
                     g[k] = d;
@@ -620,7 +621,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             float d0 = __uint_as_float(r[0]);
             if (valid) {
                 const float h0 = __half2float(*reinterpret_cast<const __half*>(smem + L::BC + tile_off(row, 16, 32)));
-                d0 += dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) * a.loss_scale;
+                d0 += dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) * loss_scale;
             }
             r[0] = __float_as_uint(d0);
             uint4 o0, o1;

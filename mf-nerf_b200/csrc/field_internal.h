@@ -80,6 +80,7 @@ struct FusedArgs {
     int rgb_act;
     // backward only
     const float* dL_dsigmas; const float* dL_drgbs; float loss_scale;
+    const float* loss_scale_dev;   // when not NULL: the (dynamic) loss scale lives in device memory (mfn_amp_*), read by every CTA
     __half* dfeats;          // level-major [16][dfeats_stride] half2, loss-scaled
     int64_t dfeats_stride;
     float4* x01;             // training: normalised positions (n,4) f32, written by the forward kernel for the scatter kernel

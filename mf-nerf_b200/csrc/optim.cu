@@ -12,9 +12,21 @@ namespace mfn {
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, __half* __restrict__ p_h, int64_t n,
             float lr, float beta1, float beta2, float eps, float bc1, float bc2, float grad_scale, const int32_t* __restrict__ skip_flag, int zero_grad,
-            const float* __restrict__ hyper) {
+            const float* __restrict__ hyper, const float* __restrict__ amp, float inv_world) {
     if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }      // per-step scalars from device memory: the launch can live in a CUDA graph
     const bool skip = skip_flag && *skip_flag != 0;
+    if (amp) {
+        // AMP state in device memory (mfn_amp_*): the loss scale is dynamic and the bias corrections count APPLIED steps only (a skipped
+        // step does not advance Adam's t -- torch.optim / GradScaler semantics).  One thread per CTA evaluates the two powers in double.
+        __shared__ float s_bc[2];
+        if (threadIdx.x == 0) {
+            const double t = (double)amp[3] + 1.0;
+            s_bc[0] = (float)(1.0 - pow((double)beta1, t)); s_bc[1] = (float)(1.0 - pow((double)beta2, t));
+        }
+        __syncthreads();
+        bc1 = s_bc[0]; bc2 = s_bc[1];
+        grad_scale = inv_world / amp[0];
+    }
     const uint64_t pol_keep = umma::policy_evict_last();   // the fp16 shadow (hash table + weights) is what the next step gathers from: keep it in L2
     const int64_t n4 = n / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -52,6 +64,21 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     }
 }
 
+// GradScaler bookkeeping after an optimiser step (torch.amp.GradScaler.update, the reference trains under Lightning precision=16):
+// overflow -> the step was skipped: scale *= backoff, growth tracker reset; otherwise the tracker advances and every `interval` good
+// steps the scale grows.  amp = {scale, growth tracker, skipped steps (total), applied steps (total)}.
+__global__ void amp_update_kernel(float* __restrict__ amp, const int32_t* __restrict__ skip_flag, float backoff, float growth, float interval,
+                                  float min_scale, float max_scale) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (skip_flag && *skip_flag != 0) {
+        amp[0] = fmaxf(amp[0] * backoff, min_scale); amp[1] = 0.f; amp[2] += 1.f;
+    } else {
+        amp[3] += 1.f;
+        const float g = amp[1] + 1.f;
+        if (g >= interval) { amp[0] = fminf(amp[0] * growth, max_scale); amp[1] = 0.f; } else amp[1] = g;
+    }
+}
+
 __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2half_rn(src[i]);
@@ -62,7 +89,8 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __res
 using namespace mfn;
 
 static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1, float beta2,
-                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
+                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream,
+                       const float* amp = nullptr, float inv_world = 1.f);
 
 extern "C" int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host) {
     if (step < 1 || !hyper_host) { set_error("mfn_adam_hyper: bad argument"); return MFN_ERR_ARG; }
@@ -86,7 +114,8 @@ extern "C" int mfn_adam_step(float* params, float* grads, float* exp_avg, float*
 }
 
 static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, float lr, float beta1, float beta2,
-                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream) {
+                       float eps, float bc1, float bc2, const float* hyper, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream,
+                       const float* amp, float inv_world) {
     if (n < 0) { set_error("mfn_adam_step: bad argument"); return MFN_ERR_ARG; }
     if (n == 0) return MFN_OK;
     if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("mfn_adam_step: null pointer"); return MFN_ERR_ARG; }
@@ -100,8 +129,25 @@ static int adam_launch(float* params, float* grads, float* exp_avg, float* exp_a
     if (blocks > cap) blocks = cap;
     ProfScope ps("adam", (cudaStream_t)stream);
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (__half*)params_h, n, lr, beta1, beta2, eps, bc1,
-                                                                    bc2, grad_scale, skip_flag, zero_grad, hyper);
+                                                                    bc2, grad_scale, skip_flag, zero_grad, hyper, amp, inv_world);
     return check_launch("mfn_adam_step", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_adam_step_amp(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* lr_dev,
+                                 float beta1, float beta2, float eps, float inv_world, const float* amp_state, const int32_t* skip_flag, int zero_grad,
+                                 void* stream) {
+    if (!lr_dev || !amp_state) { set_error("mfn_adam_step_amp: null pointer"); return MFN_ERR_ARG; }
+    return adam_launch(params, grads, exp_avg, exp_avg_sq, params_h, n, 0.f, beta1, beta2, eps, 1.f, 1.f, lr_dev, 1.f, skip_flag, zero_grad, stream, amp_state,
+                       inv_world);
+}
+
+extern "C" int mfn_amp_update(float* amp_state, const int32_t* skip_flag, float backoff, float growth, int growth_interval, float min_scale, float max_scale,
+                              void* stream) {
+    if (!amp_state || !(backoff > 0.f) || !(growth >= 1.f) || growth_interval < 1 || !(min_scale > 0.f) || max_scale < min_scale) {
+        set_error("mfn_amp_update: bad argument"); return MFN_ERR_ARG;
+    }
+    amp_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(amp_state, skip_flag, backoff, growth, (float)growth_interval, min_scale, max_scale);
+    return check_launch("mfn_amp_update", (cudaStream_t)stream);
 }
 
 extern "C" int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {

@@ -105,6 +105,12 @@ class NGPEngine:
         self.loss_terms = torch.zeros(3, device=d)
         self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
         self._adam_hyper = torch.zeros(4, device=d)              # {lr, 1 - beta1^t, 1 - beta2^t}: the optimiser's per-step scalars when it runs inside a graph
+        # AMP state on the device (GradScaler semantics: the reference trains under Lightning precision=16): {loss scale, growth tracker,
+        # skipped steps, applied steps}.  The backward kernel scales by [0], Adam unscales by it and takes its bias corrections from
+        # [3] (a skipped step does not advance t), mfn_amp_update halves the scale on overflow and doubles it after 2000 good steps.
+        self._amp = torch.tensor([float(loss_scale), 0.0, 0.0, 0.0], device=d)
+        self._amp_rule = (0.5, 2.0, 2000, 1.0, 65536.0)           # backoff, growth, growth interval, min, max (torch.amp.GradScaler defaults)
+        self._lr_on_device = None
         self.center = torch.zeros(1, 3, device=d); self.half_size = torch.full((1, 3), self.scale, device=d)
         # per-sample buffers at fixed capacity
         self.cap = int(sample_capacity) if sample_capacity else R * MAX_SAMPLES
@@ -326,18 +332,37 @@ class NGPEngine:
         n_dev = self._n_back if self._fast_front else ptr(self.n_field)
         if not self._fast_front:          # (the fused compositing kernel of the front stage has cleared the flag)
             self.overflow.zero_()
-        call("mfn_field_bwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
-             self.loss_scale, ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
+        if self._fused:
+            call("mfn_field_bwd_amp", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
+                 ptr(self._amp), ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
+        else:       # MFN_FIELD_IMPL=v1 (A/B measurements): static loss scale, the AMP state's scale is never changed (see _amp_update)
+            call("mfn_field_bwd", cfg, ptr(self.xyz_params_h), ptr(self.rgb_params_h), ptr(self.xyzs), S, n_dev, ptr(self.dL_dsigmas), ptr(self.dL_drgbs),
+                 self.loss_scale, ptr(self.grads), ptr(self.grads[self.off_rgb:]), ptr(self.overflow), ptr(self.field_ws), self.field_ws.numel(), st)
+
+    def _amp_update(self, st):
+        backoff, growth, interval, lo, hi = self._amp_rule if self._fused else (1.0, 1.0, 1 << 30, 1.0, 65536.0)
+        call("mfn_amp_update", ptr(self._amp), ptr(self.overflow), backoff, growth, int(interval), lo, hi, st)
 
     def _optimizer_step(self, lr=None):
         self.step_count += 1
-        call("mfn_adam_step", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
-             float(self.lr if lr is None else lr), 0.9, 0.999, 1e-15, self.step_count, mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 1,
-             stream_ptr(self.dev))
+        lr = float(self.lr if lr is None else lr)
+        if lr != self._lr_on_device:
+            self._adam_hyper[:1].fill_(lr); self._lr_on_device = lr
+        st = stream_ptr(self.dev)
+        call("mfn_adam_step_amp", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
+             ptr(self._adam_hyper), 0.9, 0.999, 1e-15, 1.0 / self.world_size, ptr(self._amp), ptr(self.overflow), 1, st)
+        self._amp_update(st)
 
     def _adam_from_device_scalars(self, st):
-        call("mfn_adam_step_dev", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
-             ptr(self._adam_hyper), 0.9, 0.999, 1e-15, mdist.grad_scale(self.loss_scale, 1), ptr(self.overflow), 1, st)
+        call("mfn_adam_step_amp", ptr(self.params), ptr(self.grads), ptr(self.exp_avg), ptr(self.exp_avg_sq), ptr(self.params_h), self.n_params,
+             ptr(self._adam_hyper), 0.9, 0.999, 1e-15, 1.0, ptr(self._amp), ptr(self.overflow), 1, st)
+        self._amp_update(st)
+
+    def amp_state(self):
+        """{loss_scale, skipped_steps, applied_steps} -- a step whose fp16 gradients overflowed is skipped and reported here, never silent"""
+        self._wait_comm()
+        a = self._amp.tolist()
+        return {"loss_scale": a[0], "skipped_steps": int(a[2]), "applied_steps": int(a[3])}
 
     def _upload_adam_scalars(self, lr, stream):
         """{lr, 1 - beta1^t, 1 - beta2^t} of the step being enqueued -> device memory, through a ring of pinned rows, on `stream` (the back
@@ -351,6 +376,7 @@ class NGPEngine:
         self._hyper_k += 1
         if self._hyper_used[k]:
             self._hyper_evt[k].synchronize()      # 16 steps ago: long done unless the host is that far ahead
+        self._lr_on_device = None                 # (the plain path's cached value no longer describes _adam_hyper[0])
         row = self._hyper_host[k]
         _lib.check(_lib.lib.mfn_adam_hyper(float(lr), 0.9, 0.999, int(self.step_count), ctypes.c_void_p(row.data_ptr())), "mfn_adam_hyper")
         with torch.cuda.stream(stream):
@@ -603,8 +629,7 @@ class NGPEngine:
         self.step_count += 1
         p_, g_, m_, v_, ph_ = self._adam_ptrs
         lr_ = float(self.lr if lr is None else lr)
-        if not self.collectives:
-            self._upload_adam_scalars(lr_, cs)
+        self._upload_adam_scalars(lr_, cs)
         cs.wait_event(self._cb_done)
         with torch.cuda.stream(cs):
             if self._graph is not None:
@@ -617,8 +642,9 @@ class NGPEngine:
                 self._back_done.record(cs); self._back_pending = True
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
                 torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)
-                call("mfn_adam_step", p_, g_, m_, v_, ph_, self._shard, lr_, 0.9, 0.999, 1e-15, self.step_count,
-                     mdist.grad_scale(self.loss_scale, self.world_size), ptr(self.overflow), 0, self._comm_stream_ptr)
+                call("mfn_adam_step_amp", p_, g_, m_, v_, ph_, self._shard, ptr(self._adam_hyper), 0.9, 0.999, 1e-15, 1.0 / self.world_size,
+                     ptr(self._amp), ptr(self.overflow), 0, self._comm_stream_ptr)
+                self._amp_update(self._comm_stream_ptr)
                 self.grads.zero_()
                 torch.distributed.all_gather_into_tensor(self.params_h, self._sl_ph, group=self.pg)
             self._comm_done.record(cs)
@@ -639,12 +665,12 @@ class NGPEngine:
         """copy of everything a training step mutates (bench.py restores it so that every timed region sees the same workload)"""
         self._wait_comm()
         return {"params": self.params.clone(), "params_h": self.params_h.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
-                "density_grid": self.density_grid.clone(), "density_bitfield": self.density_bitfield.clone(), "step_count": self.step_count,
+                "density_grid": self.density_grid.clone(), "density_bitfield": self.density_bitfield.clone(), "step_count": self.step_count, "_amp": self._amp.clone(),
                 "rng": torch.cuda.get_rng_state(self.dev)}
 
     def restore(self, snap):
         self._wait_comm()
-        for k in ("params", "params_h", "exp_avg", "exp_avg_sq", "density_bitfield"):
+        for k in ("params", "params_h", "exp_avg", "exp_avg_sq", "density_bitfield", "_amp"):
             getattr(self, k).copy_(snap[k])          # in place: a captured graph holds these addresses
         self.density_grid.copy_(snap["density_grid"])
         self.grads.zero_()

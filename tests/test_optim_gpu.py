@@ -75,3 +75,78 @@ def test_adam_step_matches_fused_adam_restatement():
     call("mfn_adam_step_dev", ptr(pa), ptr(ga), ptr(ma), ptr(va), ptr(pha), n, ptr(hd), 0.9, 0.999, 1e-15, scale, ptr(flag), 0, stream_ptr())
     assert torch.equal(pa, p) and torch.equal(ma, m) and torch.equal(va, v) and torch.equal(pha, ph)
     assert torch.equal(ga, g) and int((g != 0).sum()) > 0            # zero_grad = 0 leaves the gradient alone
+
+
+def test_amp_state_follows_gradscaler_semantics():
+    """mfn_adam_step_amp / mfn_amp_update (round 1 advisor finding: the bias-correction step advanced on skipped steps and a fixed loss
+    scale skipped silently for ever): the step with its scalars in the device-side AMP state equals mfn_adam_step with the same numbers;
+    an overflow skips the step, halves the scale and does NOT advance Adam's t; `growth_interval` applied steps double the scale."""
+    from mfnerf_b200._lib import call, ptr, stream_ptr
+    n = 4099
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    p = torch.rand(n, device="cuda", generator=gen) - 0.5
+    m = torch.rand(n, device="cuda", generator=gen) * 1e-2; v = torch.rand(n, device="cuda", generator=gen) * 1e-4
+    g = torch.randn(n, device="cuda", generator=gen) * 50.0
+    ph = torch.zeros(n, dtype=torch.float16, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scale, world, t = 256.0, 4, 7
+    amp = torch.tensor([scale, 3.0, 1.0, float(t - 1)], device="cuda")
+    lr = torch.tensor([3e-3], device="cuda")
+    pa, ma, va, ga, pha = p.clone(), m.clone(), v.clone(), g.clone(), ph.clone()
+    call("mfn_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(ph), n, 3e-3, 0.9, 0.999, 1e-15, t, 1.0 / (scale * world), ptr(flag), 1, stream_ptr())
+    call("mfn_adam_step_amp", ptr(pa), ptr(ga), ptr(ma), ptr(va), ptr(pha), n, ptr(lr), 0.9, 0.999, 1e-15, 1.0 / world, ptr(amp), ptr(flag), 1, stream_ptr())
+    torch.testing.assert_close(ma, m, rtol=1e-6, atol=1e-9); torch.testing.assert_close(va, v, rtol=2e-6, atol=1e-14)   # (1/world)/scale vs 1/(scale*world): 1 ulp
+    torch.testing.assert_close(pa, p, rtol=0, atol=2e-7)
+    assert int((ga != 0).sum()) == 0
+    rule = (0.5, 2.0, 4, 1.0, 1024.0)
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert amp.tolist() == [512.0, 0.0, 1.0, float(t)]                    # tracker 3 -> 4 = the interval: the scale grows, t advances
+    amp.copy_(torch.tensor([256.0, 2.0, 1.0, 6.0]))
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert amp.tolist() == [256.0, 3.0, 1.0, 7.0]                         # applied step: tracker and t advance
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert amp.tolist() == [512.0, 0.0, 1.0, 8.0]                         # 4th consecutive applied step: the scale grows
+    flag.fill_(1)
+    p0, m0, v0 = pa.clone(), ma.clone(), va.clone()
+    g2 = torch.full((n,), float("inf"), device="cuda")
+    call("mfn_adam_step_amp", ptr(pa), ptr(g2), ptr(ma), ptr(va), ptr(pha), n, ptr(lr), 0.9, 0.999, 1e-15, 1.0 / world, ptr(amp), ptr(flag), 1, stream_ptr())
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert torch.equal(pa, p0) and torch.equal(ma, m0) and torch.equal(va, v0) and int((g2 != 0).sum()) == 0
+    assert amp.tolist() == [256.0, 0.0, 2.0, 8.0]                         # skipped: scale halved, t unchanged, counted
+    amp.copy_(torch.tensor([1.0, 0.0, 0.0, 0.0]))
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert amp.tolist()[0] == 1.0                                          # clamped at min_scale
+    flag.zero_()
+    amp.copy_(torch.tensor([1024.0, 3.0, 0.0, 0.0]))
+    call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
+    assert amp.tolist()[0] == 1024.0                                       # ... and at max_scale
+
+
+def test_engine_recovers_from_overflow_and_reports_skipped_steps():
+    """a loss scale far too large overflows the fp16 gradients: the engine skips those steps (parameters untouched), halves the scale
+    until the gradients fit, then trains; skipped steps are counted, never silent"""
+    import scenes
+    import vren
+    from mfnerf_b200.engine import NGPEngine
+    eng = NGPEngine(scale=0.5, n_rays=256, sample_capacity=256 * 160, log2_T=15, loss_scale=2.0 ** 40)
+    eng.density_grid.copy_(torch.from_numpy(scenes.syn.lego_density_grid(0.5, 1)).cuda())
+    vren.packbits(eng.density_grid.reshape(-1), 0.5, eng.density_bitfield)
+    rays = scenes.scene("lego", 256, seed=3)
+    batch = torch.stack([torch.from_numpy(rays["rays_o"]), torch.from_numpy(rays["rays_d"]),
+                         scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).float()]).cuda().contiguous()
+    p0 = eng.gather_master_params().clone()
+    eng.train_step_packed(batch, global_step=1)
+    st = eng.amp_state()
+    assert st["skipped_steps"] == 1 and st["applied_steps"] == 0 and st["loss_scale"] == 2.0 ** 39
+    assert torch.equal(eng.gather_master_params(), p0)
+    first = None
+    for s in range(2, 80):
+        if s == 6:
+            eng.capture()
+        eng.train_step_packed(batch, global_step=s)
+        if s == 40:
+            eng.flush(); first = float(eng.loss_terms.sum())
+    eng.flush()
+    st = eng.amp_state()
+    assert 5 < st["skipped_steps"] < 40 and st["applied_steps"] == 79 - st["skipped_steps"] and st["loss_scale"] < 2.0 ** 34
+    assert float(eng.loss_terms.sum()) < first
