@@ -305,10 +305,10 @@ int mfn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
  * mfn_adam_hyper and upload it ahead of time): nothing in the launch changes from step to step, so it can be part of a CUDA graph. */
 int mfn_adam_hyper(float lr, float beta1, float beta2, int step, float* hyper_host);
 /* ---- AMP bookkeeping (the reference trains under Lightning precision=16: autocast + torch.amp.GradScaler, train.py:284-295) -------
- * amp_state = 4 floats in DEVICE memory {loss scale, growth tracker, skipped steps (total), applied steps (total)}; the caller
- * initialises it to {scale0, 0, 0, 0}.  mfn_field_bwd_amp scales the gradients by amp_state[0]; mfn_adam_step_amp unscales by
+ * amp_state = 8 floats in DEVICE memory {loss scale, growth tracker, skipped steps (total), applied steps (total), 1 - beta1^t and
+ * 1 - beta2^t of the next step, 2 spare}, initialised by mfn_amp_init (pageable host copy of 32 bytes + one tiny launch).  mfn_field_bwd_amp scales the gradients by amp_state[0]; mfn_adam_step_amp unscales by
  * inv_world / amp_state[0] (inv_world = 1 / number of data-parallel ranks whose gradients were summed), takes lr from lr_dev[0] and
- * the bias corrections from amp_state[3] + 1 -- a skipped step does not advance Adam's t; mfn_amp_update then applies GradScaler's
+ * the bias corrections of t = amp_state[3] + 1 from amp_state[4..5] -- a skipped step does not advance Adam's t; mfn_amp_update then applies GradScaler's
  * update rule from the overflow flag (skip -> scale *= backoff; `growth_interval` consecutive applied steps -> scale *= growth).
  * Nothing in these launches changes from step to step, so all three can sit in a CUDA graph. */
 int mfn_field_bwd_amp(const mfn_field_cfg* cfg_host, const void* xyz_params_h, const void* rgb_params_h, const float* xyzs, int64_t n_max,
@@ -317,10 +317,23 @@ int mfn_field_bwd_amp(const mfn_field_cfg* cfg_host, const void* xyz_params_h, c
 int mfn_adam_step_amp(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* lr_dev,
                       float beta1, float beta2, float eps, float inv_world, const float* amp_state, const int32_t* skip_flag, int zero_grad,
                       void* stream);
+int mfn_amp_init(float* amp_state, float loss_scale, int applied_steps, float beta1, float beta2, void* stream);
 int mfn_amp_update(float* amp_state, const int32_t* skip_flag, float backoff, float growth, int growth_interval, float min_scale,
-                   float max_scale, void* stream);
+                   float max_scale, float beta1, float beta2, void* stream);
 int mfn_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* params_h, int64_t n, const float* hyper_dev,
                       float beta1, float beta2, float eps, float grad_scale, const int32_t* skip_flag, int zero_grad, void* stream);
+/* ---- data-parallel gradient exchange + optimiser in ONE kernel over NVLink / NVSwitch peer memory (replaces DDP's bucketed NCCL
+ * all-reduce + replicated optimiser, train.py:284-285; csrc/dp_exchange.cu).  Every rank owns the shard [shard_begin, shard_begin + n)
+ * of the flat parameter vector: its kernel sums that shard of ALL ranks' gradient buffers (multimem.ld_reduce through the NVSwitch
+ * when grads_mc != 0, else `world` peer loads), clears it on every rank, applies Adam (AMP state as in mfn_adam_step_amp, inv_world =
+ * 1 / world) to its fp32 master shard and stores the fp16 shadow into EVERY rank's copy (multimem.st / peer stores).
+ * *_ptrs_host: HOST arrays of `world` peer-mapped device addresses (index = rank) of each rank's gradient buffer (f32), fp16 shadow and
+ * int32 overflow flag; *_mc: multicast addresses of the same two buffers or 0; skip_out (device, may be NULL) receives the OR of all
+ * ranks' flags.  The caller must barrier all ranks before (gradients complete) and after (shadows written) the launch. */
+int mfn_dp_exchange_adam(int world, const uint64_t* grads_ptrs_host, const uint64_t* shadow_ptrs_host, const uint64_t* flag_ptrs_host,
+                         uint64_t grads_mc, uint64_t shadow_mc, float* params_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
+                         int64_t shard_begin, int64_t n, const float* lr_dev, float beta1, float beta2, float eps, const float* amp_state,
+                         int32_t* skip_out, void* stream);
 int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream);
 
 #ifdef __cplusplus

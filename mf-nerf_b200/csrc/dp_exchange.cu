@@ -1,0 +1,126 @@
+// Data-parallel gradient exchange + optimiser as ONE kernel over NVLink / NVSwitch peer memory (the reference trains
+// with DDP, train.py:284-285: bucketed NCCL all-reduce of the flat fp32 gradients, then a replicated optimiser step on every rank).
+//
+// Here every rank owns the shard [shard_begin, shard_begin + n) of the flat parameter vector (ZeRO-1 style) and ONE kernel per rank does,
+// element by element of its shard:
+//     g      = sum over ranks of grads_r[j]            one multimem.ld_reduce (the NVSwitch adds the N copies in the fabric: 1/N of the
+//                                                      gradient bytes cross this GPU's links) -- or N peer loads when there is no multicast
+//     grads_r[j] <- 0 on every rank                    one multimem.st: the shard owner is the only reader of element j, so it can clear
+//                                                      all copies at once and no rank needs a memset before its next scatter
+//     Adam on the fp32 master copy (local HBM: p, m, v of the shard only), unscale and skip-on-overflow like optim.cu
+//     shadow_r[j] <- fp16(p) on every rank             one multimem.st: the fp16 parameters every field kernel gathers from
+// i.e. reduce-scatter + optimiser + all-gather + gradient zeroing in one pass, 4 + 2 bytes per parameter over the links instead of NCCL's
+// three collectives with the optimiser and a memset in between.  The overflow flags of all ranks are OR-ed by every CTA (N loads) so that
+// every replica takes the same skip-or-step decision (GradScaler semantics under DDP).
+//
+// Synchronisation is the caller's: every rank's gradient buffer must be complete before the kernel starts anywhere, and every rank's kernel
+// must have finished before any rank reads its shadow or accumulates new gradients -- the engine brackets the launch with two device-side
+// barriers over the same symmetric-memory allocation (torch.distributed._symmetric_memory, engine.py:_dp_setup).
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include "../../include/mfnerf_b200.h"
+
+namespace mfn {
+
+constexpr int kMaxRanks = 16;
+struct PeerPtrs { unsigned long long p[kMaxRanks]; };
+
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st_v4(void* mc, float a, float b, float c, float d) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const float4& g, float gs, float lr, float b1, float b2, float eps, float bc1, float bc2) {
+    float* P = &p.x; float* M = &m.x; float* V = &v.x; const float* G = &g.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {     // the arithmetic of optim.cu's adam_kernel, expression for expression
+        const float gr = G[k] * gs;
+        M[k] = b1 * M[k] + (1.f - b1) * gr;
+        V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+        P[k] -= lr * (M[k] / bc1) / (sqrtf(V[k] / bc2) + eps);
+    }
+}
+
+// 8 parameters per thread and iteration: two 16-byte gradient reductions, one 16-byte shadow store
+template <bool MC>
+__global__ void __launch_bounds__(256)
+dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerPtrs flags, float* grads_mc, __half* shadow_mc, int world,
+                        float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t shard_begin, int64_t n, const float* __restrict__ lr_dev,
+                        float beta1, float beta2, float eps, const float* __restrict__ amp, int32_t* __restrict__ skip_out) {
+    int bad = 0;
+    for (int r = 0; r < world; ++r) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
+    const bool skip = bad != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && skip_out) *skip_out = skip ? 1 : 0;
+    const float lr = lr_dev[0], bc1 = amp[4], bc2 = amp[5], gs = (1.f / (float)world) / amp[0];
+    const int64_t n8 = n / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = shard_begin + 8 * i;
+        float4 g0, g1;
+        if (MC) {
+            g0 = mc_ld_reduce_add(grads_mc + j); g1 = mc_ld_reduce_add(grads_mc + j + 4);
+            mc_st_v4(grads_mc + j, 0.f, 0.f, 0.f, 0.f); mc_st_v4(grads_mc + j + 4, 0.f, 0.f, 0.f, 0.f);
+        } else {
+            g0 = make_float4(0.f, 0.f, 0.f, 0.f); g1 = g0;
+            for (int r = 0; r < world; ++r) {
+                float4* gp = reinterpret_cast<float4*>(grads.p[r]) + (j >> 2);
+                const float4 a = __ldcv(gp), b = __ldcv(gp + 1);
+                g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w; g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
+                gp[0] = make_float4(0.f, 0.f, 0.f, 0.f); gp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (skip) continue;
+        float4* P = reinterpret_cast<float4*>(p) + 2 * i; float4* M = reinterpret_cast<float4*>(m) + 2 * i; float4* V = reinterpret_cast<float4*>(v) + 2 * i;
+        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];
+        adam4(p0, m0, v0, g0, gs, lr, beta1, beta2, eps, bc1, bc2);
+        adam4(p1, m1, v1, g1, gs, lr, beta1, beta2, eps, bc1, bc2);
+        P[0] = p0; P[1] = p1; M[0] = m0; M[1] = m1; V[0] = v0; V[1] = v1;
+        const __half2 h0 = __floats2half2_rn(p0.x, p0.y), h1 = __floats2half2_rn(p0.z, p0.w), h2 = __floats2half2_rn(p1.x, p1.y), h3 = __floats2half2_rn(p1.z, p1.w);
+        const float f0 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h0)), f1 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h1)),
+                    f2 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2)), f3 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h3));
+        if (MC) mc_st_v4(shadow_mc + j, f0, f1, f2, f3);      // (a store moves bits: 8 halves travel as 4 "floats")
+        else for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(reinterpret_cast<__half*>(shadow.p[r]) + j) = make_float4(f0, f1, f2, f3);
+    }
+    __threadfence_system();      // this thread's peer / multicast stores are performed system-wide before the grid can complete
+}
+
+}  // namespace mfn
+
+using namespace mfn;
+
+extern "C" int mfn_dp_exchange_adam(int world, const uint64_t* grads_ptrs_host, const uint64_t* shadow_ptrs_host, const uint64_t* flag_ptrs_host,
+                                    uint64_t grads_mc, uint64_t shadow_mc, float* params_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                    int64_t shard_begin, int64_t n, const float* lr_dev, float beta1, float beta2, float eps, const float* amp_state,
+                                    int32_t* skip_out, void* stream) {
+    if (world < 1 || world > kMaxRanks || n < 0 || shard_begin < 0 || (n % 8) || (shard_begin % 8)) {
+        set_error("mfn_dp_exchange_adam: bad argument (1 <= world <= 16, shard begin and size multiples of 8)"); return MFN_ERR_ARG;
+    }
+    if (n == 0) return MFN_OK;
+    if (!grads_ptrs_host || !shadow_ptrs_host || !flag_ptrs_host || !params_shard || !exp_avg_shard || !exp_avg_sq_shard || !lr_dev || !amp_state) {
+        set_error("mfn_dp_exchange_adam: null pointer"); return MFN_ERR_ARG;
+    }
+    if ((grads_mc != 0) != (shadow_mc != 0)) { set_error("mfn_dp_exchange_adam: give both multicast addresses or neither"); return MFN_ERR_ARG; }
+    PeerPtrs g{}, s{}, f{};
+    for (int r = 0; r < world; ++r) {
+        g.p[r] = grads_ptrs_host[r]; s.p[r] = shadow_ptrs_host[r]; f.p[r] = flag_ptrs_host[r];
+        if (!g.p[r] || !s.p[r] || !f.p[r] || (g.p[r] & 15) || (s.p[r] & 15)) { set_error("mfn_dp_exchange_adam: peer pointers must be non-null and 16-byte aligned"); return MFN_ERR_ARG; }
+    }
+    if ((grads_mc & 15) || (shadow_mc & 15) || ((uintptr_t)params_shard & 15) || ((uintptr_t)exp_avg_shard & 15) || ((uintptr_t)exp_avg_sq_shard & 15)) {
+        set_error("mfn_dp_exchange_adam: buffers must be 16-byte aligned"); return MFN_ERR_ARG;
+    }
+    int64_t blocks = ceil_div(n / 8, 256);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    ProfScope ps("adam", (cudaStream_t)stream);
+    if (grads_mc)
+        dp_exchange_adam_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, (float*)grads_mc, (__half*)shadow_mc, world, params_shard, exp_avg_shard,
+                                                                                         exp_avg_sq_shard, shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out);
+    else
+        dp_exchange_adam_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, nullptr, nullptr, world, params_shard, exp_avg_shard, exp_avg_sq_shard,
+                                                                                          shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out);
+    return check_launch("mfn_dp_exchange_adam", (cudaStream_t)stream);
+}

@@ -17,14 +17,9 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
     const bool skip = skip_flag && *skip_flag != 0;
     if (amp) {
         // AMP state in device memory (mfn_amp_*): the loss scale is dynamic and the bias corrections count APPLIED steps only (a skipped
-        // step does not advance Adam's t -- torch.optim / GradScaler semantics).  One thread per CTA evaluates the two powers in double.
-        __shared__ float s_bc[2];
-        if (threadIdx.x == 0) {
-            const double t = (double)amp[3] + 1.0;
-            s_bc[0] = (float)(1.0 - pow((double)beta1, t)); s_bc[1] = (float)(1.0 - pow((double)beta2, t));
-        }
-        __syncthreads();
-        bc1 = s_bc[0]; bc2 = s_bc[1];
+        // step does not advance Adam's t -- torch.optim / GradScaler semantics); mfn_amp_update leaves the corrections of the next
+        // step in amp[4], amp[5] (evaluated in double by one thread), so nothing here is more than a load
+        bc1 = amp[4]; bc2 = amp[5];
         grad_scale = inv_world / amp[0];
     }
     const uint64_t pol_keep = umma::policy_evict_last();   // the fp16 shadow (hash table + weights) is what the next step gathers from: keep it in L2
@@ -68,15 +63,19 @@ adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
 // overflow -> the step was skipped: scale *= backoff, growth tracker reset; otherwise the tracker advances and every `interval` good
 // steps the scale grows.  amp = {scale, growth tracker, skipped steps (total), applied steps (total)}.
 __global__ void amp_update_kernel(float* __restrict__ amp, const int32_t* __restrict__ skip_flag, float backoff, float growth, float interval,
-                                  float min_scale, float max_scale) {
+                                  float min_scale, float max_scale, float beta1, float beta2, int init_only) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (skip_flag && *skip_flag != 0) {
-        amp[0] = fmaxf(amp[0] * backoff, min_scale); amp[1] = 0.f; amp[2] += 1.f;
-    } else {
-        amp[3] += 1.f;
-        const float g = amp[1] + 1.f;
-        if (g >= interval) { amp[0] = fminf(amp[0] * growth, max_scale); amp[1] = 0.f; } else amp[1] = g;
+    if (!init_only) {
+        if (skip_flag && *skip_flag != 0) {
+            amp[0] = fmaxf(amp[0] * backoff, min_scale); amp[1] = 0.f; amp[2] += 1.f;
+        } else {
+            amp[3] += 1.f;
+            const float g = amp[1] + 1.f;
+            if (g >= interval) { amp[0] = fminf(amp[0] * growth, max_scale); amp[1] = 0.f; } else amp[1] = g;
+        }
     }
+    const double t = (double)amp[3] + 1.0;      // bias corrections of the NEXT step, in double from the float betas (apex's arithmetic)
+    amp[4] = (float)(1.0 - pow((double)beta1, t)); amp[5] = (float)(1.0 - pow((double)beta2, t));
 }
 
 __global__ void cast_f32_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
@@ -142,12 +141,20 @@ extern "C" int mfn_adam_step_amp(float* params, float* grads, float* exp_avg, fl
 }
 
 extern "C" int mfn_amp_update(float* amp_state, const int32_t* skip_flag, float backoff, float growth, int growth_interval, float min_scale, float max_scale,
-                              void* stream) {
+                              float beta1, float beta2, void* stream) {
     if (!amp_state || !(backoff > 0.f) || !(growth >= 1.f) || growth_interval < 1 || !(min_scale > 0.f) || max_scale < min_scale) {
         set_error("mfn_amp_update: bad argument"); return MFN_ERR_ARG;
     }
-    amp_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(amp_state, skip_flag, backoff, growth, (float)growth_interval, min_scale, max_scale);
+    amp_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(amp_state, skip_flag, backoff, growth, (float)growth_interval, min_scale, max_scale, beta1, beta2, 0);
     return check_launch("mfn_amp_update", (cudaStream_t)stream);
+}
+
+extern "C" int mfn_amp_init(float* amp_state, float loss_scale, int applied_steps, float beta1, float beta2, void* stream) {
+    if (!amp_state || !(loss_scale > 0.f) || applied_steps < 0) { set_error("mfn_amp_init: bad argument"); return MFN_ERR_ARG; }
+    const float h[8] = {loss_scale, 0.f, 0.f, (float)applied_steps, 0.f, 0.f, 0.f, 0.f};
+    if (cudaMemcpyAsync(amp_state, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream) != cudaSuccess) { set_error("mfn_amp_init: copy failed"); return MFN_ERR_CUDA; }
+    amp_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(amp_state, nullptr, 1.f, 1.f, 1.f, 1.f, 1.f, beta1, beta2, 1);
+    return check_launch("mfn_amp_init", (cudaStream_t)stream);
 }
 
 extern "C" int mfn_cast_f32_to_f16(const float* src, void* dst, int64_t n, void* stream) {

@@ -108,7 +108,8 @@ class NGPEngine:
         # AMP state on the device (GradScaler semantics: the reference trains under Lightning precision=16): {loss scale, growth tracker,
         # skipped steps, applied steps}.  The backward kernel scales by [0], Adam unscales by it and takes its bias corrections from
         # [3] (a skipped step does not advance t), mfn_amp_update halves the scale on overflow and doubles it after 2000 good steps.
-        self._amp = torch.tensor([float(loss_scale), 0.0, 0.0, 0.0], device=d)
+        self._amp = torch.zeros(8, device=d)
+        call("mfn_amp_init", ptr(self._amp), float(loss_scale), 0, 0.9, 0.999, stream_ptr(d))
         self._amp_rule = (0.5, 2.0, 2000, 1.0, 65536.0)           # backoff, growth, growth interval, min, max (torch.amp.GradScaler defaults)
         self._lr_on_device = None
         self.center = torch.zeros(1, 3, device=d); self.half_size = torch.full((1, 3), self.scale, device=d)
@@ -341,7 +342,7 @@ class NGPEngine:
 
     def _amp_update(self, st):
         backoff, growth, interval, lo, hi = self._amp_rule if self._fused else (1.0, 1.0, 1 << 30, 1.0, 65536.0)
-        call("mfn_amp_update", ptr(self._amp), ptr(self.overflow), backoff, growth, int(interval), lo, hi, st)
+        call("mfn_amp_update", ptr(self._amp), ptr(self.overflow), backoff, growth, int(interval), lo, hi, 0.9, 0.999, st)
 
     def _optimizer_step(self, lr=None):
         self.step_count += 1

@@ -339,6 +339,25 @@ def test_unbounded_scene_with_distortion_loss_trains_and_renders():
     torch.testing.assert_close(a["rgb"], b["rgb"], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_training_step_updates_the_occupancy_grid_exactly_once(pipelined):
+    """train.py:165-168: ONE update_density_grid per 16 steps.  Round 1's pipelined train_step() ran it twice on those steps (0.95^2 decay,
+    two field queries, the cell-sampling seed advanced twice) and no test saw it because every test stepped off the multiples of 16."""
+    rays = scenes.scene("lego", 256, seed=4)
+    o = torch.from_numpy(rays["rays_o"]).cuda(); d = torch.from_numpy(rays["rays_d"]).cuda()
+    tgt = scenes.syn.analytic_render(rays["rays_o"], rays["rays_d"]).cuda().float()
+    for step, warm in ((16, True), (256, False)):
+        a = _engine(256, pipelined=pipelined); b = _engine(256, pipelined=pipelined)
+        b.update_density_grid(warmup=warm)                       # the reference rule, once, from the same initial state
+        a.train_step(o, d, tgt, global_step=step)
+        torch.cuda.synchronize()
+        assert a._dg_calls == b._dg_calls == a.cascades
+        assert torch.equal(a.density_grid, b.density_grid) and torch.equal(a.density_bitfield, b.density_bitfield)
+        c = _engine(256, pipelined=pipelined)
+        c.train_step_packed(torch.stack([o, d, tgt]).contiguous(), global_step=step); c.flush(); torch.cuda.synchronize()
+        assert torch.equal(c.density_grid, b.density_grid)
+
+
 def test_update_density_grid_fused_kernels_follow_the_reference_rule():
     """networks.py:242-271 semantics of csrc/density_grid.cu, checked with torch on the same queried positions: jittered positions
     stay inside their cell, grid = where(grid < 0, grid, max(grid * decay, sigma)), occupied-cell draws hit occupied cells, the

@@ -90,7 +90,9 @@ def test_amp_state_follows_gradscaler_semantics():
     ph = torch.zeros(n, dtype=torch.float16, device="cuda")
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
     scale, world, t = 256.0, 4, 7
-    amp = torch.tensor([scale, 3.0, 1.0, float(t - 1)], device="cuda")
+    amp = torch.zeros(8, device="cuda")
+    call("mfn_amp_init", ptr(amp), scale, t - 1, 0.9, 0.999, stream_ptr())
+    amp[1] = 3.0; amp[2] = 1.0
     lr = torch.tensor([3e-3], device="cuda")
     pa, ma, va, ga, pha = p.clone(), m.clone(), v.clone(), g.clone(), ph.clone()
     call("mfn_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(ph), n, 3e-3, 0.9, 0.999, 1e-15, t, 1.0 / (scale * world), ptr(flag), 1, stream_ptr())
@@ -98,26 +100,26 @@ def test_amp_state_follows_gradscaler_semantics():
     torch.testing.assert_close(ma, m, rtol=1e-6, atol=1e-9); torch.testing.assert_close(va, v, rtol=2e-6, atol=1e-14)   # (1/world)/scale vs 1/(scale*world): 1 ulp
     torch.testing.assert_close(pa, p, rtol=0, atol=2e-7)
     assert int((ga != 0).sum()) == 0
-    rule = (0.5, 2.0, 4, 1.0, 1024.0)
+    rule = (0.5, 2.0, 4, 1.0, 1024.0, 0.9, 0.999)
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
-    assert amp.tolist() == [512.0, 0.0, 1.0, float(t)]                    # tracker 3 -> 4 = the interval: the scale grows, t advances
-    amp.copy_(torch.tensor([256.0, 2.0, 1.0, 6.0]))
+    assert amp.tolist()[:4] == [512.0, 0.0, 1.0, float(t)]                    # tracker 3 -> 4 = the interval: the scale grows, t advances
+    amp[:4] = torch.tensor([256.0, 2.0, 1.0, 6.0])
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
-    assert amp.tolist() == [256.0, 3.0, 1.0, 7.0]                         # applied step: tracker and t advance
+    assert amp.tolist()[:4] == [256.0, 3.0, 1.0, 7.0]                         # applied step: tracker and t advance
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
-    assert amp.tolist() == [512.0, 0.0, 1.0, 8.0]                         # 4th consecutive applied step: the scale grows
+    assert amp.tolist()[:4] == [512.0, 0.0, 1.0, 8.0]                         # 4th consecutive applied step: the scale grows
     flag.fill_(1)
     p0, m0, v0 = pa.clone(), ma.clone(), va.clone()
     g2 = torch.full((n,), float("inf"), device="cuda")
     call("mfn_adam_step_amp", ptr(pa), ptr(g2), ptr(ma), ptr(va), ptr(pha), n, ptr(lr), 0.9, 0.999, 1e-15, 1.0 / world, ptr(amp), ptr(flag), 1, stream_ptr())
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
     assert torch.equal(pa, p0) and torch.equal(ma, m0) and torch.equal(va, v0) and int((g2 != 0).sum()) == 0
-    assert amp.tolist() == [256.0, 0.0, 2.0, 8.0]                         # skipped: scale halved, t unchanged, counted
-    amp.copy_(torch.tensor([1.0, 0.0, 0.0, 0.0]))
+    assert amp.tolist()[:4] == [256.0, 0.0, 2.0, 8.0]                         # skipped: scale halved, t unchanged, counted
+    amp[:4] = torch.tensor([1.0, 0.0, 0.0, 0.0])
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
     assert amp.tolist()[0] == 1.0                                          # clamped at min_scale
     flag.zero_()
-    amp.copy_(torch.tensor([1024.0, 3.0, 0.0, 0.0]))
+    amp[:4] = torch.tensor([1024.0, 3.0, 0.0, 0.0])
     call("mfn_amp_update", ptr(amp), ptr(flag), *rule, stream_ptr())
     assert amp.tolist()[0] == 1024.0                                       # ... and at max_scale
 
