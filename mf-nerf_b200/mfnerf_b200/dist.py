@@ -86,3 +86,39 @@ def agreed_warmup(step, world_size, device, seconds, chunk=128, max_chunks=64, g
         if stop:
             break
     return n
+
+
+class SymmetricBuffers:
+    """[fp32 gradients | fp16 shadow parameters | int32 overflow flag] of one rank in ONE symmetric-memory allocation
+    (torch.distributed._symmetric_memory: the same virtual layout on every rank, every rank's copy peer-mapped over NVLink, and one
+    NVSwitch multicast address for the whole allocation where the fabric supports it).  Gives csrc/dp_exchange.cu its pointer tables and the
+    device-side barriers that bracket the exchange kernel."""
+
+    def __init__(self, n_params, device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass                                    # newer torch: rendezvous() enables it by itself
+        world = dist.get_world_size(group)
+        al = lambda b: (b + 255) // 256 * 256
+        off_g, off_s = 0, al(4 * n_params)
+        off_f = off_s + al(2 * n_params)
+        total = off_f + 256
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.grads = self.buf[off_g:off_g + 4 * n_params].view(torch.float32)
+        self.shadow = self.buf[off_s:off_s + 2 * n_params].view(torch.float16)
+        self.flag = self.buf[off_f:off_f + 4].view(torch.int32)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        arr = lambda off: (ctypes.c_uint64 * world)(*[b + off for b in base])
+        self.grads_ptrs, self.shadow_ptrs, self.flag_ptrs = arr(off_g), arr(off_s), arr(off_f)
+        mc = int(self.hdl.multicast_ptr) if (getattr(self.hdl, "has_multicast_support", False) and os.environ.get("MFN_DP_MULTICAST", "1") != "0") else 0
+        self.grads_mc, self.shadow_mc = (mc + off_g, mc + off_s) if mc else (0, 0)
+        self.multicast = bool(mc)
+
+    def barrier(self, channel):
+        """device-side barrier of all ranks on the current stream (signal pads of the symmetric allocation)"""
+        self.hdl.barrier(channel=channel)

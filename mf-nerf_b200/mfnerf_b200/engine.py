@@ -11,6 +11,7 @@ stream (tests compare the two).  Rendering is the device-side wavefront of csrc/
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -77,8 +78,18 @@ class NGPEngine:
         p[self.n_mlp1:self.n_xyz].uniform_(-1e-4, 1e-4, generator=g)
         _init_mlp(p[self.off_rgb:self.off_rgb + self.n_rgb], 32, rgb_channels, rgb_layers, 16, g)
         self.params = p.to(d)
-        self.params_h = self.params.half()
-        self.grads = torch.zeros_like(self.params)
+        # Data-parallel: gradients, fp16 shadow parameters and the overflow flag live in ONE symmetric-memory allocation (peer-mapped on
+        # every rank, NVSwitch multicast where available) so that the gradient exchange + optimiser is one kernel over NVLink
+        # (csrc/dp_exchange.cu).  MFN_DP_EXCHANGE=nccl keeps the three NCCL collectives (A/B measurements, fabrics without P2P).
+        self._symm = None
+        if world_size > 1 and os.environ.get("MFN_DP_EXCHANGE", "fused") == "fused":
+            self._symm = mdist.SymmetricBuffers(self.n_params, d, process_group)
+        if self._symm is not None:
+            self.params_h, self.grads, self.overflow = self._symm.shadow, self._symm.grads, self._symm.flag
+            self.params_h.copy_(self.params); self.grads.zero_(); self.overflow.zero_()
+        else:
+            self.params_h = self.params.half()
+            self.grads = torch.zeros_like(self.params)
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.step_count = 0
@@ -103,7 +114,9 @@ class NGPEngine:
         self.dL_dopacity, self.dL_ddepth, self.dL_drgb = f(R), torch.zeros(R, device=d), f(R, 3)
         self.dist_loss, self.dL_ddist = f(R), f(R)
         self.loss_terms = torch.zeros(3, device=d)
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
+        if self._symm is None:
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=d)
+        self._skip = torch.zeros(1, dtype=torch.int32, device=d)  # fused exchange: the OR of all ranks' overflow flags (what mfn_amp_update reads)
         self._adam_hyper = torch.zeros(4, device=d)              # {lr, 1 - beta1^t, 1 - beta2^t}: the optimiser's per-step scalars when it runs inside a graph
         # AMP state on the device (GradScaler semantics: the reference trains under Lightning precision=16): {loss scale, growth tracker,
         # skipped steps, applied steps}.  The backward kernel scales by [0], Adam unscales by it and takes its bias corrections from
@@ -639,7 +652,17 @@ class NGPEngine:
                 self._field_back()
                 if not self.collectives:
                     self._adam_from_device_scalars(self._comm_stream_ptr)
-            if self.collectives:
+            if self.collectives and self._symm is not None:
+                # ONE kernel: sum this rank's shard of every rank's gradients through the NVSwitch, clear it everywhere, Adam on the fp32
+                # master shard, fp16 shadow stored into every rank's copy -- bracketed by two device-side barriers over the symmetric allocation
+                self._back_done.record(cs); self._back_pending = True
+                sy = self._symm
+                sy.barrier(0)                  # every rank's field backward + scatter has landed in its gradient buffer
+                call("mfn_dp_exchange_adam", self.world_size, sy.grads_ptrs, sy.shadow_ptrs, sy.flag_ptrs, sy.grads_mc, sy.shadow_mc, p_, m_, v_,
+                     self._rank * self._shard, self._shard, ptr(self._adam_hyper), 0.9, 0.999, 1e-15, ptr(self._amp), ptr(self._skip), self._comm_stream_ptr)
+                call("mfn_amp_update", ptr(self._amp), ptr(self._skip), *self._amp_rule, 0.9, 0.999, self._comm_stream_ptr)
+                sy.barrier(1)                  # every rank's shadow stores are visible: the next field forward may gather, the next scatter may accumulate
+            elif self.collectives:
                 self._back_done.record(cs); self._back_pending = True
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
                 torch.distributed.all_reduce(self.overflow, op=torch.distributed.ReduceOp.MAX, group=self.pg)

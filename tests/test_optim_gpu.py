@@ -152,3 +152,60 @@ def test_engine_recovers_from_overflow_and_reports_skipped_steps():
     st = eng.amp_state()
     assert 5 < st["skipped_steps"] < 40 and st["applied_steps"] == 79 - st["skipped_steps"] and st["loss_scale"] < 2.0 ** 34
     assert float(eng.loss_terms.sum()) < first
+
+
+def test_fused_exchange_kernel_emulated_ranks():
+    """mfn_dp_exchange_adam (csrc/dp_exchange.cu), peer-pointer path, with the ranks EMULATED on one GPU (the guide's rule when there are
+    fewer GPUs than ranks): world = 3 gradient / shadow / flag buffers in local memory, one launch per rank's shard.  Expected: every shard
+    of every buffer summed, cleared and Adam-stepped exactly like mfn_adam_step_amp on the pre-summed gradient; all shadows identical; the
+    overflow flag of ANY rank skips the step everywhere but still clears the gradients.  (The multicast path needs a multi-GPU box:
+    tools/dp_exchange_check.py under torchrun.)"""
+    import ctypes
+    from mfnerf_b200._lib import call, ptr, stream_ptr
+    world, n = 3, 3 * 8 * 1000
+    shard = n // world
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    p = torch.rand(n, device="cuda", generator=gen) - 0.5
+    m = torch.rand(n, device="cuda", generator=gen) * 1e-2; v = torch.rand(n, device="cuda", generator=gen) * 1e-4
+    grads = [torch.randn(n, device="cuda", generator=gen) * 40.0 for _ in range(world)]
+    shadows = [torch.zeros(n, dtype=torch.float16, device="cuda") for _ in range(world)]
+    flags = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    amp = torch.zeros(8, device="cuda"); call("mfn_amp_init", ptr(amp), 512.0, 4, 0.9, 0.999, stream_ptr())
+    lr = torch.tensor([5e-3], device="cuda")
+    arr = lambda ts: (ctypes.c_uint64 * world)(*[t.data_ptr() for t in ts])
+    # reference: the plain sharded path -- sum, then mfn_adam_step_amp
+    pr, mr, vr = p.clone(), m.clone(), v.clone()
+    gsum = torch.stack(grads).sum(0)            # (fp32 sum in rank order, like the kernel's loop)
+    gs = grads[0].clone()
+    for g in grads[1:]:
+        gs += g
+    shr = torch.zeros(n, dtype=torch.float16, device="cuda")
+    call("mfn_adam_step_amp", ptr(pr), ptr(gs), ptr(mr), ptr(vr), ptr(shr), n, ptr(lr), 0.9, 0.999, 1e-15, 1.0 / world, ptr(amp), None, 0, stream_ptr())
+    skip = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    for r in range(world):      # "rank r" steps its shard
+        sl = slice(r * shard, (r + 1) * shard)
+        call("mfn_dp_exchange_adam", world, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p[sl]), ptr(m[sl]), ptr(v[sl]), r * shard, shard,
+             ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), ptr(skip), stream_ptr())
+    torch.cuda.synchronize()
+    assert int(skip) == 0 and all(int((g != 0).sum()) == 0 for g in grads)
+    torch.testing.assert_close(m, mr, rtol=1e-6, atol=1e-9); torch.testing.assert_close(v, vr, rtol=2e-6, atol=1e-14)
+    torch.testing.assert_close(p, pr, rtol=0, atol=2e-7)
+    for s in shadows:
+        assert torch.equal(s, p.half())
+    del gsum
+    # any rank's overflow flag: nothing moves anywhere, gradients still cleared, the decision is published
+    for g in grads:
+        g.normal_(generator=gen)
+    flags[2].fill_(1)
+    p0, m0, v0, s0 = p.clone(), m.clone(), v.clone(), shadows[0].clone()
+    for r in range(world):
+        sl = slice(r * shard, (r + 1) * shard)
+        call("mfn_dp_exchange_adam", world, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p[sl]), ptr(m[sl]), ptr(v[sl]), r * shard, shard,
+             ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), ptr(skip), stream_ptr())
+    torch.cuda.synchronize()
+    assert int(skip) == 1 and torch.equal(p, p0) and torch.equal(m, m0) and torch.equal(v, v0) and torch.equal(shadows[1], s0)
+    assert all(int((g != 0).sum()) == 0 for g in grads)
+    # argument checks
+    from mfnerf_b200._lib import lib
+    assert lib.mfn_dp_exchange_adam(world, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p), ptr(m), ptr(v), 4, shard, ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), None, None) == -2
+    assert lib.mfn_dp_exchange_adam(17, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p), ptr(m), ptr(v), 0, shard, ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), None, None) == -2
