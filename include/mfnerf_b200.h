@@ -325,11 +325,12 @@ int mfn_adam_step_dev(float* params, float* grads, float* exp_avg, float* exp_av
 /* ---- data-parallel gradient exchange + optimiser in ONE kernel over NVLink / NVSwitch peer memory (replaces DDP's bucketed NCCL
  * all-reduce + replicated optimiser, train.py:284-285; csrc/dp_exchange.cu).  Every rank owns the shard [shard_begin, shard_begin + n)
  * of the flat parameter vector: its kernel sums that shard of ALL ranks' gradient buffers (multimem.ld_reduce through the NVSwitch
- * when grads_mc != 0, else `world` peer loads), clears it on every rank, applies Adam (AMP state as in mfn_adam_step_amp, inv_world =
+ * when grads_mc != 0, else `world` peer loads), applies Adam (AMP state as in mfn_adam_step_amp, inv_world =
  * 1 / world) to its fp32 master shard and stores the fp16 shadow into EVERY rank's copy (multimem.st / peer stores).
  * *_ptrs_host: HOST arrays of `world` peer-mapped device addresses (index = rank) of each rank's gradient buffer (f32), fp16 shadow and
  * int32 overflow flag; *_mc: multicast addresses of the same two buffers or 0; skip_out (device, may be NULL) receives the OR of all
- * ranks' flags.  The caller must barrier all ranks before (gradients complete) and after (shadows written) the launch. */
+ * ranks' flags (set: nothing is updated).  The caller must barrier all ranks before (gradients complete) and after (shadows written)
+ * the launch, and clears its own gradient buffer after the second barrier. */
 int mfn_dp_exchange_adam(int world, const uint64_t* grads_ptrs_host, const uint64_t* shadow_ptrs_host, const uint64_t* flag_ptrs_host,
                          uint64_t grads_mc, uint64_t shadow_mc, float* params_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
                          int64_t shard_begin, int64_t n, const float* lr_dev, float beta1, float beta2, float eps, const float* amp_state,

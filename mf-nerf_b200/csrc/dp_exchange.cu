@@ -5,12 +5,11 @@
 // element by element of its shard:
 //     g      = sum over ranks of grads_r[j]            one multimem.ld_reduce (the NVSwitch adds the N copies in the fabric: 1/N of the
 //                                                      gradient bytes cross this GPU's links) -- or N peer loads when there is no multicast
-//     grads_r[j] <- 0 on every rank                    one multimem.st: the shard owner is the only reader of element j, so it can clear
-//                                                      all copies at once and no rank needs a memset before its next scatter
 //     Adam on the fp32 master copy (local HBM: p, m, v of the shard only), unscale and skip-on-overflow like optim.cu
 //     shadow_r[j] <- fp16(p) on every rank             one multimem.st: the fp16 parameters every field kernel gathers from
-// i.e. reduce-scatter + optimiser + all-gather + gradient zeroing in one pass, 4 + 2 bytes per parameter over the links instead of NCCL's
-// three collectives with the optimiser and a memset in between.  The overflow flags of all ranks are OR-ed by every CTA (N loads) so that
+// i.e. reduce-scatter + optimiser + all-gather in one pass, 4 + 2 bytes per parameter over the links instead of NCCL's three collectives
+// with the optimiser in between (every rank clears its own gradient buffer locally after the closing barrier: clearing all copies from
+// the owner -- tried first -- doubles the store traffic on the links).  The overflow flags of all ranks are OR-ed by every CTA (N loads) so that
 // every replica takes the same skip-or-step decision (GradScaler semantics under DDP).
 //
 // Synchronisation is the caller's: every rank's gradient buffer must be complete before the kernel starts anywhere, and every rank's kernel
@@ -45,8 +44,10 @@ __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const flo
     }
 }
 
-// 8 parameters per thread and iteration: two 16-byte gradient reductions, one 16-byte shadow store
-template <bool MC>
+// 8 parameters per thread and iteration: two 16-byte gradient reductions, one 16-byte shadow store.  W = number of ranks when it is
+// 2, 4 or 8 (all peer loads of an iteration are issued before the first one is consumed: one NVLink round trip per iteration instead
+// of W), 0 = any other count (runtime loop).  MC: multimem path.
+template <bool MC, int W>
 __global__ void __launch_bounds__(256)
 dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerPtrs flags, float* grads_mc, __half* shadow_mc, int world,
                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t shard_begin, int64_t n, const float* __restrict__ lr_dev,
@@ -55,26 +56,32 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
     for (int r = 0; r < world; ++r) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
     const bool skip = bad != 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && skip_out) *skip_out = skip ? 1 : 0;
+    if (skip) return;           // nothing moves anywhere; the caller clears its own gradient buffer after the closing barrier either way
     const float lr = lr_dev[0], bc1 = amp[4], bc2 = amp[5], gs = (1.f / (float)world) / amp[0];
     const int64_t n8 = n / 8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = shard_begin + 8 * i;
+        float4* P = reinterpret_cast<float4*>(p) + 2 * i; float4* M = reinterpret_cast<float4*>(m) + 2 * i; float4* V = reinterpret_cast<float4*>(v) + 2 * i;
         float4 g0, g1;
         if (MC) {
             g0 = mc_ld_reduce_add(grads_mc + j); g1 = mc_ld_reduce_add(grads_mc + j + 4);
-            mc_st_v4(grads_mc + j, 0.f, 0.f, 0.f, 0.f); mc_st_v4(grads_mc + j + 4, 0.f, 0.f, 0.f, 0.f);
+        } else if (W > 0) {
+            constexpr int WW = W > 0 ? W : 1;
+            float4 a[WW], b[WW];
+#pragma unroll
+            for (int r = 0; r < WW; ++r) { const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2); a[r] = __ldcv(gp); b[r] = __ldcv(gp + 1); }
+            g0 = a[0]; g1 = b[0];
+#pragma unroll
+            for (int r = 1; r < WW; ++r) { g0.x += a[r].x; g0.y += a[r].y; g0.z += a[r].z; g0.w += a[r].w; g1.x += b[r].x; g1.y += b[r].y; g1.z += b[r].z; g1.w += b[r].w; }
         } else {
             g0 = make_float4(0.f, 0.f, 0.f, 0.f); g1 = g0;
             for (int r = 0; r < world; ++r) {
-                float4* gp = reinterpret_cast<float4*>(grads.p[r]) + (j >> 2);
+                const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2);
                 const float4 a = __ldcv(gp), b = __ldcv(gp + 1);
                 g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w; g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
-                gp[0] = make_float4(0.f, 0.f, 0.f, 0.f); gp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (skip) continue;
-        float4* P = reinterpret_cast<float4*>(p) + 2 * i; float4* M = reinterpret_cast<float4*>(m) + 2 * i; float4* V = reinterpret_cast<float4*>(v) + 2 * i;
-        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];
+        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];       // (local HBM: in flight together with the peer loads)
         adam4(p0, m0, v0, g0, gs, lr, beta1, beta2, eps, bc1, bc2);
         adam4(p1, m1, v1, g1, gs, lr, beta1, beta2, eps, bc1, bc2);
         P[0] = p0; P[1] = p1; M[0] = m0; M[1] = m1; V[0] = v0; V[1] = v1;
@@ -82,9 +89,14 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
         const float f0 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h0)), f1 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h1)),
                     f2 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2)), f3 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h3));
         if (MC) mc_st_v4(shadow_mc + j, f0, f1, f2, f3);      // (a store moves bits: 8 halves travel as 4 "floats")
-        else for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(reinterpret_cast<__half*>(shadow.p[r]) + j) = make_float4(f0, f1, f2, f3);
+        else {
+#pragma unroll
+            for (int r = 0; r < (W > 0 ? W : kMaxRanks); ++r)
+                if (W > 0 || r < world) *reinterpret_cast<float4*>(reinterpret_cast<__half*>(shadow.p[r]) + j) = make_float4(f0, f1, f2, f3);
+        }
     }
-    __threadfence_system();      // this thread's peer / multicast stores are performed system-wide before the grid can complete
+    // no fence here: the stores are performed before the grid completes, and the barrier kernel that follows on the same stream publishes
+    // them to the peers (a system-scope fence per thread cost more than the whole exchange: 194 us -> see DESIGN.md section 6)
 }
 
 }  // namespace mfn
@@ -116,11 +128,13 @@ extern "C" int mfn_dp_exchange_adam(int world, const uint64_t* grads_ptrs_host, 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     ProfScope ps("adam", (cudaStream_t)stream);
-    if (grads_mc)
-        dp_exchange_adam_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, (float*)grads_mc, (__half*)shadow_mc, world, params_shard, exp_avg_shard,
-                                                                                         exp_avg_sq_shard, shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out);
-    else
-        dp_exchange_adam_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, nullptr, nullptr, world, params_shard, exp_avg_shard, exp_avg_sq_shard,
-                                                                                          shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out);
+#define MFN_DPX(MC_, W_) dp_exchange_adam_kernel<MC_, W_><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, (float*)grads_mc, (__half*)shadow_mc, world, \
+        params_shard, exp_avg_shard, exp_avg_sq_shard, shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out)
+    if (grads_mc) MFN_DPX(true, 0);
+    else if (world == 2) MFN_DPX(false, 2);
+    else if (world == 4) MFN_DPX(false, 4);
+    else if (world == 8) MFN_DPX(false, 8);
+    else MFN_DPX(false, 0);
+#undef MFN_DPX
     return check_launch("mfn_dp_exchange_adam", (cudaStream_t)stream);
 }

@@ -661,7 +661,8 @@ class NGPEngine:
                 call("mfn_dp_exchange_adam", self.world_size, sy.grads_ptrs, sy.shadow_ptrs, sy.flag_ptrs, sy.grads_mc, sy.shadow_mc, p_, m_, v_,
                      self._rank * self._shard, self._shard, ptr(self._adam_hyper), 0.9, 0.999, 1e-15, ptr(self._amp), ptr(self._skip), self._comm_stream_ptr)
                 call("mfn_amp_update", ptr(self._amp), ptr(self._skip), *self._amp_rule, 0.9, 0.999, self._comm_stream_ptr)
-                sy.barrier(1)                  # every rank's shadow stores are visible: the next field forward may gather, the next scatter may accumulate
+                sy.barrier(1)                  # every rank's shadow stores are visible and every rank has read this rank's gradients
+                self.grads.zero_()             # (local HBM; clearing all copies from the shard owner doubles the NVLink store traffic)
             elif self.collectives:
                 self._back_done.record(cs); self._back_pending = True
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)

@@ -157,8 +157,8 @@ def test_engine_recovers_from_overflow_and_reports_skipped_steps():
 def test_fused_exchange_kernel_emulated_ranks():
     """mfn_dp_exchange_adam (csrc/dp_exchange.cu), peer-pointer path, with the ranks EMULATED on one GPU (the guide's rule when there are
     fewer GPUs than ranks): world = 3 gradient / shadow / flag buffers in local memory, one launch per rank's shard.  Expected: every shard
-    of every buffer summed, cleared and Adam-stepped exactly like mfn_adam_step_amp on the pre-summed gradient; all shadows identical; the
-    overflow flag of ANY rank skips the step everywhere but still clears the gradients.  (The multicast path needs a multi-GPU box:
+    of every buffer summed and Adam-stepped exactly like mfn_adam_step_amp on the pre-summed gradient; all shadows identical; the
+    overflow flag of ANY rank skips the step everywhere.  (The multicast path needs a multi-GPU box:
     tools/dp_exchange_check.py under torchrun.)"""
     import ctypes
     from mfnerf_b200._lib import call, ptr, stream_ptr
@@ -187,13 +187,13 @@ def test_fused_exchange_kernel_emulated_ranks():
         call("mfn_dp_exchange_adam", world, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p[sl]), ptr(m[sl]), ptr(v[sl]), r * shard, shard,
              ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), ptr(skip), stream_ptr())
     torch.cuda.synchronize()
-    assert int(skip) == 0 and all(int((g != 0).sum()) == 0 for g in grads)
+    assert int(skip) == 0
     torch.testing.assert_close(m, mr, rtol=1e-6, atol=1e-9); torch.testing.assert_close(v, vr, rtol=2e-6, atol=1e-14)
     torch.testing.assert_close(p, pr, rtol=0, atol=2e-7)
     for s in shadows:
         assert torch.equal(s, p.half())
     del gsum
-    # any rank's overflow flag: nothing moves anywhere, gradients still cleared, the decision is published
+    # any rank's overflow flag: nothing moves anywhere, the decision is published
     for g in grads:
         g.normal_(generator=gen)
     flags[2].fill_(1)
@@ -204,7 +204,6 @@ def test_fused_exchange_kernel_emulated_ranks():
              ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), ptr(skip), stream_ptr())
     torch.cuda.synchronize()
     assert int(skip) == 1 and torch.equal(p, p0) and torch.equal(m, m0) and torch.equal(v, v0) and torch.equal(shadows[1], s0)
-    assert all(int((g != 0).sum()) == 0 for g in grads)
     # argument checks
     from mfnerf_b200._lib import lib
     assert lib.mfn_dp_exchange_adam(world, arr(grads), arr(shadows), arr(flags), 0, 0, ptr(p), ptr(m), ptr(v), 4, shard, ptr(lr), 0.9, 0.999, 1e-15, ptr(amp), None, None) == -2
