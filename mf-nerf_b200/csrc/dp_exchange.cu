@@ -52,9 +52,16 @@ __global__ void __launch_bounds__(256)
 dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerPtrs flags, float* grads_mc, __half* shadow_mc, int world,
                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t shard_begin, int64_t n, const float* __restrict__ lr_dev,
                         float beta1, float beta2, float eps, const float* __restrict__ amp, int32_t* __restrict__ skip_out) {
-    int bad = 0;
-    for (int r = 0; r < world; ++r) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
-    const bool skip = bad != 0;
+    // one thread per CTA reads the ranks' overflow flags (every thread doing so put 300 k uncached loads of ONE peer address on the links:
+    // that, not the data, was most of the first version's 194 us)
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        for (int r = 0; r < world; ++r) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
+        s_bad = bad;
+    }
+    __syncthreads();
+    const bool skip = s_bad != 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && skip_out) *skip_out = skip ? 1 : 0;
     if (skip) return;           // nothing moves anywhere; the caller clears its own gradient buffer after the closing barrier either way
     const float lr = lr_dev[0], bc1 = amp[4], bc2 = amp[5], gs = (1.f / (float)world) / amp[0];
@@ -62,6 +69,7 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = shard_begin + 8 * i;
         float4* P = reinterpret_cast<float4*>(p) + 2 * i; float4* M = reinterpret_cast<float4*>(m) + 2 * i; float4* V = reinterpret_cast<float4*>(v) + 2 * i;
+        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];       // local HBM, requested first: in flight together with the peer loads
         float4 g0, g1;
         if (MC) {
             g0 = mc_ld_reduce_add(grads_mc + j); g1 = mc_ld_reduce_add(grads_mc + j + 4);
@@ -69,7 +77,7 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
             constexpr int WW = W > 0 ? W : 1;
             float4 a[WW], b[WW];
 #pragma unroll
-            for (int r = 0; r < WW; ++r) { const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2); a[r] = __ldcv(gp); b[r] = __ldcv(gp + 1); }
+            for (int r = 0; r < WW; ++r) { const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2); a[r] = __ldcs(gp); b[r] = __ldcs(gp + 1); }
             g0 = a[0]; g1 = b[0];
 #pragma unroll
             for (int r = 1; r < WW; ++r) { g0.x += a[r].x; g0.y += a[r].y; g0.z += a[r].z; g0.w += a[r].w; g1.x += b[r].x; g1.y += b[r].y; g1.z += b[r].z; g1.w += b[r].w; }
@@ -77,11 +85,10 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
             g0 = make_float4(0.f, 0.f, 0.f, 0.f); g1 = g0;
             for (int r = 0; r < world; ++r) {
                 const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2);
-                const float4 a = __ldcv(gp), b = __ldcv(gp + 1);
+                const float4 a = __ldcs(gp), b = __ldcs(gp + 1);
                 g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w; g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
             }
         }
-        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];       // (local HBM: in flight together with the peer loads)
         adam4(p0, m0, v0, g0, gs, lr, beta1, beta2, eps, bc1, bc2);
         adam4(p1, m1, v1, g1, gs, lr, beta1, beta2, eps, bc1, bc2);
         P[0] = p0; P[1] = p1; M[0] = m0; M[1] = m1; V[0] = v0; V[1] = v1;
