@@ -545,7 +545,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": workload, "name": args.config, "engine": {k: v for k, v in ekw.items()}, "n_params": int(eng.n_params),
-                       "rays_per_step_per_gpu": R, "parallelism": f"ray-sharded dp{world}" + (" + NCCL all-reduce of fp32 grads" if world > 1 else ""),
+                       "rays_per_step_per_gpu": R, "parallelism": f"ray-sharded dp{world}" + ("" if world == 1 else (" + fused NVLink exchange kernel (reduce-scatter + Adam + all-gather, "
+                                                                    + ("NVSwitch multimem" if eng._symm.multicast else "peer loads/stores") + ")") if eng._symm is not None
+                                                                    else " + NCCL reduce-scatter / sharded Adam / all-gather"),
                        "density_grid_update_every": 16, "optimizer": "fused Adam eps=1e-15 inside the timed region", "cuda_graph": not args.no_graph,
                        "extra_untimed_warmup_steps": extra_warmup,
                        "l2": f"per-step working set (fp32 params+grads+Adam moments {16 * eng.n_params / 1e6:.0f} MB, fp16 table {2 * eng.n_params / 1e6:.0f} MB, sample "

@@ -115,7 +115,11 @@ class SymmetricBuffers:
         base = [int(p) for p in self.hdl.buffer_ptrs]
         arr = lambda off: (ctypes.c_uint64 * world)(*[b + off for b in base])
         self.grads_ptrs, self.shadow_ptrs, self.flag_ptrs = arr(off_g), arr(off_s), arr(off_f)
-        mc = int(self.hdl.multicast_ptr) if (getattr(self.hdl, "has_multicast_support", False) and os.environ.get("MFN_DP_MULTICAST", "1") != "0") else 0
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st) pays from 4 ranks on; between 2 GPUs the in-fabric reduction is slower than
+        # two peer loads (measured on 2 x B200, 11.4 M parameters: 192 us vs 89 us).  MFN_DP_MULTICAST=1 / 0 forces the choice.
+        want = os.environ.get("MFN_DP_MULTICAST", "auto")
+        use_mc = getattr(self.hdl, "has_multicast_support", False) and (want == "1" or (want == "auto" and world >= 4))
+        mc = int(self.hdl.multicast_ptr) if use_mc else 0
         self.grads_mc, self.shadow_mc = (mc + off_g, mc + off_s) if mc else (0, 0)
         self.multicast = bool(mc)
 
