@@ -17,6 +17,7 @@
 // barriers over the same symmetric-memory allocation (torch.distributed._symmetric_memory, engine.py:_dp_setup).
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "../../include/mfnerf_b200.h"
 
 namespace mfn {
@@ -44,10 +45,12 @@ __device__ __forceinline__ void adam4(float4& p, float4& m, float4& v, const flo
     }
 }
 
-// 8 parameters per thread and iteration: two 16-byte gradient reductions, one 16-byte shadow store.  W = number of ranks when it is
-// 2, 4 or 8 (all peer loads of an iteration are issued before the first one is consumed: one NVLink round trip per iteration instead
-// of W), 0 = any other count (runtime loop).  MC: multimem path.
-template <bool MC, int W>
+// One "chunk" = 8 parameters: two 16-byte gradient reductions, one 16-byte shadow store.  A thread handles U chunks per iteration and
+// issues ALL their loads (local p, m, v and the W peers' / the multicast gradients: ~16 sixteen-byte requests) before consuming the first,
+// so that a SMALL grid -- one CTA per SM by default, like a collective library's channels -- keeps the links busy and leaves the SMs to the
+// marching front that overlaps the exchange (a full-size grid made both slower).  W = number of ranks when it is 2, 4 or 8, 0 = any other
+// count (runtime loop, U = 1).  MC: multimem path.
+template <bool MC, int W, int U>
 __global__ void __launch_bounds__(256)
 dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerPtrs flags, float* grads_mc, __half* shadow_mc, int world,
                         float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t shard_begin, int64_t n, const float* __restrict__ lr_dev,
@@ -66,44 +69,65 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
     if (skip) return;           // nothing moves anywhere; the caller clears its own gradient buffer after the closing barrier either way
     const float lr = lr_dev[0], bc1 = amp[4], bc2 = amp[5], gs = (1.f / (float)world) / amp[0];
     const int64_t n8 = n / 8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t j = shard_begin + 8 * i;
-        float4* P = reinterpret_cast<float4*>(p) + 2 * i; float4* M = reinterpret_cast<float4*>(m) + 2 * i; float4* V = reinterpret_cast<float4*>(v) + 2 * i;
-        float4 p0 = P[0], p1 = P[1], m0 = M[0], m1 = M[1], v0 = V[0], v1 = V[1];       // local HBM, requested first: in flight together with the peer loads
-        float4 g0, g1;
-        if (MC) {
-            g0 = mc_ld_reduce_add(grads_mc + j); g1 = mc_ld_reduce_add(grads_mc + j + 4);
-        } else if (W > 0) {
-            constexpr int WW = W > 0 ? W : 1;
-            float4 a[WW], b[WW];
+    constexpr int WW = W > 0 ? W : 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += stride * U) {
+        float4 pp[U][2], mm[U][2], vv[U][2], g[U][2];
+        float4 a[U][WW][2];
 #pragma unroll
-            for (int r = 0; r < WW; ++r) { const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2); a[r] = __ldcs(gp); b[r] = __ldcs(gp + 1); }
-            g0 = a[0]; g1 = b[0];
+        for (int u = 0; u < U; ++u) {      // chunk u of this thread: i0 + u * stride (coalesced across the warp for every u)
+            const int64_t i = i0 + u * stride;
+            if (i < n8) {
+                const int64_t j = shard_begin + 8 * i;
+                pp[u][0] = reinterpret_cast<const float4*>(p)[2 * i]; pp[u][1] = reinterpret_cast<const float4*>(p)[2 * i + 1];
+                mm[u][0] = reinterpret_cast<const float4*>(m)[2 * i]; mm[u][1] = reinterpret_cast<const float4*>(m)[2 * i + 1];
+                vv[u][0] = reinterpret_cast<const float4*>(v)[2 * i]; vv[u][1] = reinterpret_cast<const float4*>(v)[2 * i + 1];
+                if (MC) { g[u][0] = mc_ld_reduce_add(grads_mc + j); g[u][1] = mc_ld_reduce_add(grads_mc + j + 4); }
+                else if (W > 0) {
 #pragma unroll
-            for (int r = 1; r < WW; ++r) { g0.x += a[r].x; g0.y += a[r].y; g0.z += a[r].z; g0.w += a[r].w; g1.x += b[r].x; g1.y += b[r].y; g1.z += b[r].z; g1.w += b[r].w; }
-        } else {
-            g0 = make_float4(0.f, 0.f, 0.f, 0.f); g1 = g0;
-            for (int r = 0; r < world; ++r) {
-                const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2);
-                const float4 a = __ldcs(gp), b = __ldcs(gp + 1);
-                g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w; g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
+                    for (int r = 0; r < WW; ++r) { const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2); a[u][r][0] = __ldcs(gp); a[u][r][1] = __ldcs(gp + 1); }
+                } else {
+                    g[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); g[u][1] = g[u][0];
+                    for (int r = 0; r < world; ++r) {
+                        const float4* gp = reinterpret_cast<const float4*>(grads.p[r]) + (j >> 2);
+                        const float4 x = __ldcs(gp), y = __ldcs(gp + 1);
+                        g[u][0].x += x.x; g[u][0].y += x.y; g[u][0].z += x.z; g[u][0].w += x.w; g[u][1].x += y.x; g[u][1].y += y.y; g[u][1].z += y.z; g[u][1].w += y.w;
+                    }
+                }
             }
         }
-        adam4(p0, m0, v0, g0, gs, lr, beta1, beta2, eps, bc1, bc2);
-        adam4(p1, m1, v1, g1, gs, lr, beta1, beta2, eps, bc1, bc2);
-        P[0] = p0; P[1] = p1; M[0] = m0; M[1] = m1; V[0] = v0; V[1] = v1;
-        const __half2 h0 = __floats2half2_rn(p0.x, p0.y), h1 = __floats2half2_rn(p0.z, p0.w), h2 = __floats2half2_rn(p1.x, p1.y), h3 = __floats2half2_rn(p1.z, p1.w);
-        const float f0 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h0)), f1 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h1)),
-                    f2 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2)), f3 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h3));
-        if (MC) mc_st_v4(shadow_mc + j, f0, f1, f2, f3);      // (a store moves bits: 8 halves travel as 4 "floats")
-        else {
 #pragma unroll
-            for (int r = 0; r < (W > 0 ? W : kMaxRanks); ++r)
-                if (W > 0 || r < world) *reinterpret_cast<float4*>(reinterpret_cast<__half*>(shadow.p[r]) + j) = make_float4(f0, f1, f2, f3);
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n8) break;
+            const int64_t j = shard_begin + 8 * i;
+            if (!MC && W > 0) {
+                g[u][0] = a[u][0][0]; g[u][1] = a[u][0][1];
+#pragma unroll
+                for (int r = 1; r < WW; ++r) {      // rank order: the same sum on every run
+                    g[u][0].x += a[u][r][0].x; g[u][0].y += a[u][r][0].y; g[u][0].z += a[u][r][0].z; g[u][0].w += a[u][r][0].w;
+                    g[u][1].x += a[u][r][1].x; g[u][1].y += a[u][r][1].y; g[u][1].z += a[u][r][1].z; g[u][1].w += a[u][r][1].w;
+                }
+            }
+            adam4(pp[u][0], mm[u][0], vv[u][0], g[u][0], gs, lr, beta1, beta2, eps, bc1, bc2);
+            adam4(pp[u][1], mm[u][1], vv[u][1], g[u][1], gs, lr, beta1, beta2, eps, bc1, bc2);
+            reinterpret_cast<float4*>(p)[2 * i] = pp[u][0]; reinterpret_cast<float4*>(p)[2 * i + 1] = pp[u][1];
+            reinterpret_cast<float4*>(m)[2 * i] = mm[u][0]; reinterpret_cast<float4*>(m)[2 * i + 1] = mm[u][1];
+            reinterpret_cast<float4*>(v)[2 * i] = vv[u][0]; reinterpret_cast<float4*>(v)[2 * i + 1] = vv[u][1];
+            const __half2 h0 = __floats2half2_rn(pp[u][0].x, pp[u][0].y), h1 = __floats2half2_rn(pp[u][0].z, pp[u][0].w),
+                          h2 = __floats2half2_rn(pp[u][1].x, pp[u][1].y), h3 = __floats2half2_rn(pp[u][1].z, pp[u][1].w);
+            const float f0 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h0)), f1 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h1)),
+                        f2 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2)), f3 = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h3));
+            if (MC) mc_st_v4(shadow_mc + j, f0, f1, f2, f3);      // (a store moves bits: 8 halves travel as 4 "floats")
+            else {
+#pragma unroll
+                for (int r = 0; r < (W > 0 ? W : kMaxRanks); ++r)
+                    if (W > 0 || r < world) *reinterpret_cast<float4*>(reinterpret_cast<__half*>(shadow.p[r]) + j) = make_float4(f0, f1, f2, f3);
+            }
         }
     }
     // no fence here: the stores are performed before the grid completes, and the barrier kernel that follows on the same stream publishes
-    // them to the peers (a system-scope fence per thread cost more than the whole exchange: 194 us -> see DESIGN.md section 6)
+    // them to the peers (a system-scope fence per thread cost more than the rest of the kernel)
 }
 
 }  // namespace mfn
@@ -130,18 +154,19 @@ extern "C" int mfn_dp_exchange_adam(int world, const uint64_t* grads_ptrs_host, 
     if ((grads_mc & 15) || (shadow_mc & 15) || ((uintptr_t)params_shard & 15) || ((uintptr_t)exp_avg_shard & 15) || ((uintptr_t)exp_avg_sq_shard & 15)) {
         set_error("mfn_dp_exchange_adam: buffers must be 16-byte aligned"); return MFN_ERR_ARG;
     }
+    static int ctas = 0;
+    if (ctas == 0) { const char* e = getenv("MFN_DPX_CTAS"); ctas = e ? atoi(e) : kNumSMs; if (ctas < 1) ctas = kNumSMs; }
     int64_t blocks = ceil_div(n / 8, 256);
-    const int64_t cap = (int64_t)kNumSMs * 8;
-    if (blocks > cap) blocks = cap;
+    if (blocks > ctas) blocks = ctas;
     if (blocks < 1) blocks = 1;
     ProfScope ps("adam", (cudaStream_t)stream);
-#define MFN_DPX(MC_, W_) dp_exchange_adam_kernel<MC_, W_><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, (float*)grads_mc, (__half*)shadow_mc, world, \
-        params_shard, exp_avg_shard, exp_avg_sq_shard, shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out)
-    if (grads_mc) MFN_DPX(true, 0);
-    else if (world == 2) MFN_DPX(false, 2);
-    else if (world == 4) MFN_DPX(false, 4);
-    else if (world == 8) MFN_DPX(false, 8);
-    else MFN_DPX(false, 0);
+#define MFN_DPX(MC_, W_, U_) dp_exchange_adam_kernel<MC_, W_, U_><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, s, f, (float*)grads_mc, (__half*)shadow_mc, \
+        world, params_shard, exp_avg_shard, exp_avg_sq_shard, shard_begin, n, lr_dev, beta1, beta2, eps, amp_state, skip_out)
+    if (grads_mc) MFN_DPX(true, 0, 4);
+    else if (world == 2) MFN_DPX(false, 2, 4);
+    else if (world == 4) MFN_DPX(false, 4, 2);
+    else if (world == 8) MFN_DPX(false, 8, 1);
+    else MFN_DPX(false, 0, 1);
 #undef MFN_DPX
     return check_launch("mfn_dp_exchange_adam", (cudaStream_t)stream);
 }
