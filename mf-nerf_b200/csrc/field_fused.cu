@@ -413,31 +413,38 @@ constexpr int kBwdThreads = 288;        // 8 epilogue warps (two threads per sam
                                         // per-row prefetch waited ~1.5 k cycles when the issuing thread was also a row thread)
 constexpr int kBwdIssuer = 256;
 
-// TMEM (fp32 dgrad accumulator) -> mask with relu'(activation tile row) -> fp16 dZ row written IN PLACE of the activation row
+// TMEM (fp32 dgrad accumulator) -> mask with relu'(activation tile row) -> fp16 dZ row written IN PLACE of the activation row.
+// The activation tile is also an operand of the weight-gradient MMAs issued right behind the dgrad MMA (dW = A^T . dZ_prev), so the
+// epilogue runs in two halves: TMEM load, mask and packing into registers as soon as the DGRAD accumulator is complete (bar_mma), the
+// stores only once the weight-gradient MMAs have finished reading the tile (bar_dw) -- their issue and execution (8 MMAs) overlap the
+// first half instead of sitting on the stage's critical path.
 template <int C>
-__device__ __forceinline__ void mask_epilogue32(uint32_t taddr, unsigned char* tile, int row, int col0) {
-    uint32_t r[32];
-    tmem_ld_x32(taddr + col0, r);
-    tmem_ld_wait();
+__device__ __forceinline__ void mask_epilogue(uint32_t taddr, unsigned char* tile, int row, int hsel, uint64_t* bar_dw, uint32_t& ph_dw) {
+    constexpr int Q = C / 64;
+    uint4 o[Q][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        uint4* p = reinterpret_cast<uint4*>(tile + tile_off(row, col0 + c * 8, C));
-        const uint4 act = *p;
-        const __half2* ah = reinterpret_cast<const __half2*>(&act);
-        uint4 o;
-        uint32_t* ow = &o.x;
+    for (int q = 0; q < Q; ++q) {
+        const int col0 = hsel * (C / 2) + 32 * q;
+        uint32_t r[32];
+        tmem_ld_x32(taddr + col0, r);
+        tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 av = __half22float2(ah[k]);
-            ow[k] = pack2(av.x > 0.f ? __uint_as_float(r[8 * c + 2 * k]) : 0.f, av.y > 0.f ? __uint_as_float(r[8 * c + 2 * k + 1]) : 0.f);
+        for (int c = 0; c < 4; ++c) {
+            const uint4 act = *reinterpret_cast<const uint4*>(tile + tile_off(row, col0 + c * 8, C));
+            const __half2* ah = reinterpret_cast<const __half2*>(&act);
+            uint32_t* ow = &o[q][c].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 av = __half22float2(ah[k]);
+                ow[k] = pack2(av.x > 0.f ? __uint_as_float(r[8 * c + 2 * k]) : 0.f, av.y > 0.f ? __uint_as_float(r[8 * c + 2 * k + 1]) : 0.f);
+            }
         }
-        *p = o;
     }
-}
-template <int C>
-__device__ __forceinline__ void mask_epilogue(uint32_t taddr, unsigned char* tile, int row, int hsel) {
+    mbar_wait(bar_dw, ph_dw); ph_dw ^= 1u;
 #pragma unroll
-    for (int q = 0; q < C / 64; ++q) mask_epilogue32<C>(taddr, tile, row, hsel * (C / 2) + 32 * q);
+    for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(tile + tile_off(row, hsel * (C / 2) + 32 * q + c * 8, C)) = o[q][c];
 }
 
 // phase timestamps of CTA 0 / thread 0 of the backward kernel (tools/fwd_phases.py): after every MMA-completion wait and every barrier
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kBwdThreads, Lay<RW>::BwdCtas)
 field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     using L = Lay<RW>;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma, bar_load[2];
+    __shared__ uint64_t bar_mma, bar_dw, bar_tail, bar_load[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kFT - 1), hsel = tid >> 7;   // two threads per sample row: they split the accumulator columns (hsel == 2: issuer warp)
@@ -461,7 +468,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     const uint64_t pol_stream = policy_evict_first();
     const float loss_scale = a.loss_scale_dev ? *a.loss_scale_dev : a.loss_scale;
     if (issuer) {
-        mbar_init(&bar_mma, 1); mbar_init(&bar_load[0], 1); mbar_init(&bar_load[1], 1); mbar_fence_init();
+        mbar_init(&bar_mma, 1); mbar_init(&bar_dw, 1); mbar_init(&bar_tail, 1); mbar_init(&bar_load[0], 1); mbar_init(&bar_load[1], 1); mbar_fence_init();
         if ((int64_t)blockIdx.x < n_tiles) {      // first X tile: in flight while the weights are staged
             mbar_arrive_expect_tx(&bar_load[0], kBlobX);
             bulk_g2s_hint(smem + L::BX, a.blobs + (size_t)blockIdx.x * kBlobX, kBlobX, &bar_load[0], pol_stream);
@@ -479,7 +486,7 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
     const uint32_t sH1 = sbase + L::BH1, sC = sbase + L::BC, sH2 = sbase + L::BH2, sH3 = sbase + L::BH3, sDZo = sbase + L::BDZo;
     const uint32_t sHL = (NH2 == 2) ? sH3 : sH2;                  // last hidden activation of the rgb net
     unsigned char* pHL = smem + ((NH2 == 2) ? L::BH3 : L::BH2);
-    uint32_t ph_mma = 0, ph_load0 = 0, ph_load1 = 0;
+    uint32_t ph_mma = 0, ph_dw = 0, ph_tail = 0, ph_load0 = 0, ph_load1 = 0;
     uint32_t acc = 0;                                              // 0 on the CTA's first tile: weight-gradient MMAs overwrite
     bool bad = false;
     // per-row inputs of a tile, requested one tile ahead (their latency used to open every tile: ~1.5 k of its ~12 k cycles):
@@ -503,8 +510,8 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         const bool valid = worker && i < n;
         const int xbuf = tile_no & 1;
         const uint32_t sX = sbase + L::BX + xbuf * kBlobX;
-        if (issuer && tile + gridDim.x < n_tiles) {   // prefetch the NEXT tile's X into the other buffer (its last reader, stage E of the
-                                                         // previous tile, finished before the barrier that ended that tile)
+        if (issuer && tile_no > 0) { mbar_wait(&bar_tail, ph_tail); ph_tail ^= 1u; }   // the previous tile's last MMAs (dW1) have read its X buffer
+        if (issuer && tile + gridDim.x < n_tiles) {   // prefetch the NEXT tile's X into the other buffer = the previous tile's
             mbar_arrive_expect_tx(&bar_load[xbuf ^ 1], kBlobX);
             bulk_g2s_hint(smem + L::BX + (xbuf ^ 1) * kBlobX, a.blobs + (size_t)(tile + gridDim.x) * kBlobX, kBlobX, &bar_load[xbuf ^ 1], pol_stream);
         }
@@ -585,11 +592,12 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         if (issuer) {
             tc_fence_after();
             mma_f16_ss(tbase + L::AccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + L::W5, RW, 0), idesc_f16(128, RW, false, true), 0u);
-            mma_chain(tbase + L::AccW5, desc_mnmajor(sHL, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(RW, 16, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
+            mma_chain(tbase + L::AccW5, desc_mnmajor(sHL, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(RW, 16, true, true), kFT / 16, acc);
+            mma_commit(&bar_dw);
         }
         MFN_MMA_WAIT();
-        if (worker) mask_epilogue<RW>(trow + L::AccH, pHL, row, hsel);                  // dZ of the last hidden layer, in place
+        if (worker) mask_epilogue<RW>(trow + L::AccH, pHL, row, hsel, &bar_dw, ph_dw);   // dZ of the last hidden layer, in place
         MFN_STAGE_SYNC();
         // next tile's per-row inputs: requested right AFTER a stage boundary -- the proxy fence of a boundary waits for the thread's
         // outstanding global loads (measured: +1.5 k cycles when they were issued just before one), the MMA wait that follows hides them
@@ -599,19 +607,21 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
             if (issuer) {
                 tc_fence_after();
                 mma_chain(tbase + L::AccH, desc_kmajor(sH3, RW, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W4, RW, 0), kstep_mnmajor(RW), idesc_f16(128, RW, false, true), RW / 16, 0u);
-                mma_chain(tbase + L::AccW4, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sH3, RW, 0), kstep_mnmajor(RW), idesc_f16(RW, RW, true, true), kFT / 16, acc);
                 mma_commit(&bar_mma);
+                mma_chain(tbase + L::AccW4, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sH3, RW, 0), kstep_mnmajor(RW), idesc_f16(RW, RW, true, true), kFT / 16, acc);
+                mma_commit(&bar_dw);
             }
             MFN_MMA_WAIT();
-            if (worker) mask_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel);    // dZ3 in place of H2
+            if (worker) mask_epilogue<RW>(trow + L::AccH, smem + L::BH2, row, hsel, &bar_dw, ph_dw);    // dZ3 in place of H2
             MFN_STAGE_SYNC();
         }
         // ---- stage C: dCAT = dZ3 . W3 (32 columns) ;  dW3 += dZ3^T . CAT
         if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sH2, RW, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W3, 32, 0), kstep_mnmajor(32), idesc_f16(128, 32, false, true), RW / 16, 0u);
-            mma_chain(tbase + L::AccW3, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sC, 32, 0), kstep_mnmajor(32), idesc_f16(RW, 32, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
+            // (dW3 reads dZ3 and CAT, which nothing writes before the next tile: no barrier of its own -- every later commit covers it)
+            mma_chain(tbase + L::AccW3, desc_mnmajor(sH2, RW, 0), kstep_mnmajor(RW), desc_mnmajor(sC, 32, 0), kstep_mnmajor(32), idesc_f16(RW, 32, true, true), kFT / 16, acc);
         }
         MFN_MMA_WAIT();
         if (hsel == 0) {   // dh = dCAT[:, 16:32] ; dh[0] += loss_scale * dL/dsigma * exp(clamp(h0, -15, 15))   (TruncExp backward)
@@ -635,18 +645,22 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         if (issuer) {
             tc_fence_after();
             mma_f16_ss(tbase + L::AccH, desc_kmajor(sDZo, 16, 0), desc_mnmajor(sbase + L::W2, 64, 0), idesc_f16(128, 64, false, true), 0u);
-            mma_chain(tbase + L::AccW2, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(64, 16, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
+            mma_chain(tbase + L::AccW2, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sDZo, 16, 0), kstep_mnmajor(16), idesc_f16(64, 16, true, true), kFT / 16, acc);
+            mma_commit(&bar_dw);
         }
         MFN_MMA_WAIT();
-        if (worker) mask_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel);        // dZ1 in place of H1
+        if (worker) mask_epilogue<64>(trow + L::AccH, smem + L::BH1, row, hsel, &bar_dw, ph_dw);        // dZ1 in place of H1
         MFN_STAGE_SYNC();
         // ---- stage E: dX = dZ1 . W1 (32 columns) ;  dW1 += dZ1^T . X
         if (issuer) {
             tc_fence_after();
             mma_chain(tbase + L::AccH, desc_kmajor(sH1, 64, 0), kstep_kmajor(), desc_mnmajor(sbase + L::W1, 32, 0), kstep_mnmajor(32), idesc_f16(128, 32, false, true), 4, 0u);
-            mma_chain(tbase + L::AccW1, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sX, 32, 0), kstep_mnmajor(32), idesc_f16(64, 32, true, true), kFT / 16, acc);
             mma_commit(&bar_mma);
+            // dW1 reads dZ1 (H1 buffer) and this tile's X buffer.  H1 is written again by the next tile's first epilogue, behind a commit
+            // that covers dW1; the X buffer by the bulk copy the issuer starts at the top of the next tile -- after waiting on bar_tail
+            mma_chain(tbase + L::AccW1, desc_mnmajor(sH1, 64, 0), kstep_mnmajor(64), desc_mnmajor(sX, 32, 0), kstep_mnmajor(32), idesc_f16(64, 32, true, true), kFT / 16, acc);
+            mma_commit(&bar_tail);
         }
         MFN_MMA_WAIT();
         if (worker) {   // dX row -> dfeats, level-major [16][stride] half2: coalesced here and in the scatter kernel; each thread of a row does 8 levels
@@ -669,6 +683,9 @@ field_bwd_fused_kernel(const __grid_constant__ FusedArgs a) {
         MFN_STAGE_SYNC();   // generic reads/writes of the tile area are ordered before the next tile's writes and bulk copy
     }
     if (bad && a.overflow) *a.overflow = 1;
+    if (issuer && tile_no > 0) mbar_wait(&bar_tail, ph_tail);      // the last tile's trailing weight-gradient MMAs have landed in TMEM
+    tc_fence_before();
+    __syncthreads();
     // ---- flush this CTA's weight-gradient accumulators.  M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16;
     //      M = 128 accumulators: row m lives in lane m.
     float* part = a.partials + (size_t)blockIdx.x * L::NumWg;
