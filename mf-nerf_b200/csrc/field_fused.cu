@@ -32,6 +32,7 @@
 #include "sh4.cuh"
 #include "umma.cuh"
 #include <stdlib.h>
+#include <atomic>
 
 namespace mfn {
 using namespace umma;
@@ -96,16 +97,29 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // (gx + xb), so the corners (x, x+1) of one (y, z) -- same 32-byte sector 7 times out of 8 -- are requested by the same load
 // instruction: a warp's gather touches <= 16 sectors instead of <= 32, and the L1 sector (tag) rate is what bounds this phase
 // (profiles/l2_peaks_r02.json: 1 divergent sector per SM per clock).  fp32 trilinear interpolation; returns the pair's sum.
+// Instruction diet (the phase is issue-bound once 5 CTAs per SM hide the latency): floor() without the conversion pipe -- for
+// |p| < 2^22, t = RZ(p + 1.5 * 2^23) is an integer-valued float in [2^23, 2^24) whose low mantissa bits ARE floor(p), so
+// floor(p) = bits(t) - 0x4B400000 (one integer add) and (float)floor(p) = t - 1.5 * 2^23 (exact): two fp32-pipe operations
+// instead of FRND + F2I on the quarter-rate pipe, same values bit for bit; 32-bit entry indices (offset + index < 2^32) so that
+// an address is one IMAD.WIDE.
+__device__ __forceinline__ float floor_split(float p, int& i) {
+    const float t = __fadd_rz(p, 12582912.f);
+    i = __float_as_int(t) - 0x4B400000;
+    return __fsub_rn(t, 12582912.f);
+}
+// one level in two halves so that the caller can put the loads of SEVERAL levels in flight before consuming any of them (the
+// phase is a chain of L2 round trips per thread: its length is what a tile's gather costs)
+struct LevelW { float wx, wy, wz; };
 template <bool MIXED>
-__device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb, uint64_t pol) {
+__device__ __forceinline__ LevelW level_indices(const GridMeta& m, int l, float x, float y, float z, int xb, uint32_t (&idx)[4]) {
     const float s = m.scale[l];
-    const uint32_t res = m.res[l], off = m.offset[l], size = m.size[l];
+    const uint32_t off = m.offset[l], size = m.size[l];
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
-    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    const float wx = px - fx, wy = py - fy, wz = pz - fz;
-    const uint32_t cx = (uint32_t)(int)fx + (uint32_t)xb, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-    const uint32_t* lvl = table + off;
-    uint32_t idx[4];
+    int ix, iy, iz;
+    const float fx = floor_split(px, ix), fy = floor_split(py, iy), fz = floor_split(pz, iz);
+    LevelW w;
+    w.wx = px - fx; w.wy = py - fy; w.wz = pz - fz;
+    const uint32_t cx = (uint32_t)ix + (uint32_t)xb, gy = (uint32_t)iy, gz = (uint32_t)iz;
     if (MIXED) {   // MixedFeature grid: vertices are hashed by their canonical-grid coordinates (grid_common.cuh: canon_vertex); the
                    // lane pair still splits the x corners, it just no longer finds them in one sector
         const float r = m.canon[l];
@@ -118,7 +132,7 @@ __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict
         const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
         idx[0] = (cx ^ hy0 ^ hz0) & mask; idx[1] = (cx ^ hy1 ^ hz0) & mask; idx[2] = (cx ^ hy0 ^ hz1) & mask; idx[3] = (cx ^ hy1 ^ hz1) & mask;
     } else {                                  // dense: x + y*res + z*res^2, mod size (only a corner on the x/y/z == res border wraps)
-        const uint32_t r2 = res * res;
+        const uint32_t res = m.res[l], r2 = res * res;
         const uint32_t b = cx + gy * res + gz * r2;
         idx[0] = b; idx[1] = b + res; idx[2] = b + r2; idx[3] = b + res + r2;
         if (idx[3] >= size) {
@@ -126,12 +140,15 @@ __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict
             for (int c = 0; c < 4; ++c) idx[c] %= size;
         }
     }
-    uint32_t v[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = ldg_nc_hint(lvl + idx[c], pol);   // the table is to stay L2-resident (evict_last)
-    const float wxs = xb ? wx : 1.f - wx;
-    const float a0 = wxs * (1.f - wy), a1 = wxs * wy;
-    const float w[4] = {a0 * (1.f - wz), a1 * (1.f - wz), a0 * wz, a1 * wz};
+    for (int c = 0; c < 4; ++c) idx[c] += off;
+    return w;
+}
+// fp32 trilinear interpolation of this lane's 4 corners, summed over the lane pair
+__device__ __forceinline__ uint32_t level_interp(const uint32_t (&v)[4], const LevelW& lw, int xb) {
+    const float wxs = xb ? lw.wx : 1.f - lw.wx;
+    const float a0 = wxs * (1.f - lw.wy), a1 = wxs * lw.wy;
+    const float w[4] = {a0 * (1.f - lw.wz), a1 * (1.f - lw.wz), a0 * lw.wz, a1 * lw.wz};
     float f0 = 0.f, f1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -141,6 +158,14 @@ __device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict
     f0 += __shfl_xor_sync(0xffffffffu, f0, 1);
     f1 += __shfl_xor_sync(0xffffffffu, f1, 1);
     return pack2(f0, f1);
+}
+template <bool MIXED>
+__device__ __forceinline__ uint32_t gather_level_pair(const uint32_t* __restrict__ table, const GridMeta& m, int l, float x, float y, float z, int xb, uint64_t pol) {
+    uint32_t idx[4], v[4];
+    const LevelW lw = level_indices<MIXED>(m, l, x, y, z, xb, idx);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = ldg_nc_hint(table + idx[c], pol);   // the table is to stay L2-resident (evict_last)
+    return level_interp(v, lw, xb);
 }
 
 // SH (degree 4) of the normalised direction mapped like networks.py:145-146 -> 16 fp16 values = CAT[:, 0:16] of one row
@@ -221,9 +246,27 @@ __host__ __device__ constexpr uint32_t kstep_mnmajor(int C) { return 2u * (uint3
 // 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107).
 // 256 threads: thread t works on sample row t % 128 (= its TMEM lane); the two threads of a row split the 16 grid levels in the
 // gather phase and the accumulator columns in the hidden-layer epilogues.
+// scheduler slots: {next tile, CTAs that have left}; zero at module load and zero again after every launch (the last leaver resets)
+constexpr int kSchedSlots = 64;
+__device__ unsigned int g_tile_sched[kSchedSlots][2];
+__device__ __forceinline__ void sched_leave(unsigned int* sched) {
+    if (!sched) return;
+    __threadfence();
+    if (atomicInc(sched + 1, gridDim.x - 1u) == gridDim.x - 1u) { sched[0] = 0u; __threadfence(); }   // atomicInc wraps the leaver count to 0 itself
+}
 constexpr int kFwdThreads = 256;
+#ifndef MFN_GATHER_TWO
+#define MFN_GATHER_TWO 0
+#endif
+constexpr bool kGatherTwoLevels = MFN_GATHER_TWO != 0;
 // phase timestamps of CTA 0 (tools/fwd_phases.py): a.dbg != nullptr only in that tool
 #define MFN_TS(k) do { if (a.dbg && blockIdx.x == 0 && tid == (k >= 100 ? 255 : 0) && tile_no < 12) a.dbg[tile_no * 16 + (k % 100)] = clock64(); } while (0)
+
+// kernel entry / exit of every CTA (tools/fwd_phases.py): dbg[1024 + 4 * cta + {0: entry ns, 1: exit ns, 2: SM id, 3: tiles done}]
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ uint32_t sm_id() { uint32_t v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#define MFN_EDGE_IN() do { if (a.dbg && tid == 0) { long long* e_ = a.dbg + 1024 + 4 * blockIdx.x; e_[0] = global_ns(); e_[2] = sm_id(); } } while (0)
+#define MFN_EDGE_OUT() do { if (a.dbg && tid == 0) { long long* e_ = a.dbg + 1024 + 4 * blockIdx.x; e_[1] = global_ns(); e_[3] = tile_no; } } while (0)
 
 template <int NH2, int MODE, bool MIXED, int RW>
 __global__ void __launch_bounds__(kFwdThreads, Lay<RW>::FwdCtas)
@@ -243,7 +286,18 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const int64_t n = a.n_dev ? min((int64_t)*a.n_dev, a.n_max) : a.n_max;
     const int64_t n_tiles = (n + kFT - 1) / kFT;
     if (TRAIN && a.n_out && blockIdx.x == 0 && tid == 0) *a.n_out = (int32_t)n;     // the backward pass's own copy of the count
-    if ((int64_t)blockIdx.x >= n_tiles) return;      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
+    // Dynamic tile scheduler: tiles are handed out by a global counter (a.sched[0]) instead of the static stride blockIdx.x + k * gridDim.x.
+    // With 5 CTAs per SM and 6.5 tiles per CTA the static split left an SM with 4, 3, ... resident CTAs for the last tile time
+    // (CTAs with 6 tiles done, CTAs with 7 not: measured 115 us of SM time for 97 us of work); the next tile is requested one tile
+    // ahead, so the atomic's latency is never waited for.  The last CTA to leave resets the counter (a.sched[1] counts leavers).
+    __shared__ int next_tile_s;
+    if (tid == 0) next_tile_s = a.sched ? (int)atomicAdd(a.sched, 1u) : (int)blockIdx.x;
+    __syncthreads();
+    if (next_tile_s >= n_tiles) {      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
+        if (tid == 0) sched_leave(a.sched);
+        return;
+    }
+    MFN_EDGE_IN();      // the grid is sized for n_max; with a device-side count most CTAs may have nothing to do
     stage_all_weights<NH2, RW>(smem, a, tid, kFwdThreads, RGB);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&tmem_base_s, nCols);
@@ -259,9 +313,11 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
     int tile_no = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_no) {
+    for (int64_t tile = next_tile_s; tile < n_tiles; tile = next_tile_s, ++tile_no) {
         const int64_t i = tile * kFT + row;
         const bool valid = i < n;
+        int tile_after = (int)tile + (int)gridDim.x;
+        if (a.sched && tid == 0) tile_after = (int)atomicAdd(a.sched, 1u);    // consumed at the end of this tile
         MFN_TS(0);
         // ---- hash-grid gather -> X tile: lane pair (2p, 2p+1) of warp w works on row 16w + p, all 16 levels
         {
@@ -276,10 +332,27 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
                 z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
                 if (TRAIN && xb == 1) a.x01[gi] = make_float4(x, y, z, 0.f);
             }
+            // feature pair of level l = columns 2l, 2l+1 of row `grow`: core matrix l / 4, byte 4 * (l % 4) of the row's 16-byte chunk;
+            // lane xb of the pair stores the levels of its parity
+            unsigned char* xrow = smem + oT + tile_off(grow, 0, 32) + 4 * xb;
 #pragma unroll 2
-            for (int l = 0; l < 16; ++l) {
-                const uint32_t v = gather_level_pair<MIXED>(table, m, l, x, y, z, xb, pol_keep);    // (invalid rows gather entry 0 harmlessly)
-                if (xb == (l & 1)) *reinterpret_cast<uint32_t*>(smem + oT + tile_off(grow, 2 * l, 32)) = gvalid ? v : 0u;
+            for (int l = 0; l < 16; l += 2) {
+                uint32_t v0, v1;
+                if (kGatherTwoLevels) {      // 8 loads in flight per thread (invalid rows gather entry 0 harmlessly)
+                    uint32_t i0[4], i1[4];
+                    const LevelW w0 = level_indices<MIXED>(m, l, x, y, z, xb, i0);
+                    const LevelW w1 = level_indices<MIXED>(m, l + 1, x, y, z, xb, i1);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) i0[c] = ldg_nc_hint(table + i0[c], pol_keep);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) i1[c] = ldg_nc_hint(table + i1[c], pol_keep);
+                    v0 = level_interp(i0, w0, xb);
+                    v1 = level_interp(i1, w1, xb);
+                } else {
+                    v0 = gather_level_pair<MIXED>(table, m, l, x, y, z, xb, pol_keep);
+                    v1 = gather_level_pair<MIXED>(table, m, l + 1, x, y, z, xb, pol_keep);
+                }
+                *reinterpret_cast<uint32_t*>(xrow + (l >> 2) * 128 + (l & 2) * 4) = gvalid ? (xb ? v1 : v0) : 0u;
             }
         }
         MFN_TS(1); MFN_TS(109);
@@ -342,6 +415,7 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         }
         phase ^= 1u;
         MFN_TS(6);
+        if (!RGB && tid == 0) next_tile_s = tile_after;
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -397,10 +471,13 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             }
         }
         phase ^= 1u;
+        if (tid == 0) next_tile_s = tile_after;
         tc_fence_before();
         __syncthreads();   // TMEM and the tile region are free for the next tile
         MFN_TS(8);
     }
+    MFN_EDGE_OUT();
+    if (tid == 0) sched_leave(a.sched);
     if (TRAIN && tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
@@ -757,7 +834,15 @@ static void launch_fwd_m(const FusedArgs& a, const GridMeta& m, cudaStream_t st)
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) { const char* e = getenv("MFN_FWD_CTAS"); ctas_per_sm = e ? atoi(e) : max_ctas; if (ctas_per_sm < 1 || ctas_per_sm > max_ctas) ctas_per_sm = max_ctas; }
     const int64_t cap = ctas_per_sm * (int64_t)num_sms();
-    field_fwd_fused_kernel<NH2, MODE, MIXED, RW><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(a, m);
+    // one scheduler slot per launch, 16 per mode in rotation: launches of one mode that are in flight at the same time (different
+    // streams) never share a slot unless 16 of them overlap; a captured launch keeps its slot, its replays are stream-ordered
+    static unsigned int* sched_base = nullptr;
+    static std::atomic<unsigned> seq{0};
+    static const bool dynamic = !(getenv("MFN_FWD_STATIC") && atoi(getenv("MFN_FWD_STATIC")));
+    if (!sched_base) { void* p = nullptr; if (cudaGetSymbolAddress(&p, g_tile_sched) == cudaSuccess) sched_base = (unsigned int*)p; }
+    FusedArgs b = a;
+    b.sched = (dynamic && sched_base) ? sched_base + 2 * (MODE * 16 + (seq.fetch_add(1) & 15u)) : nullptr;
+    field_fwd_fused_kernel<NH2, MODE, MIXED, RW><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(b, m);
 }
 template <int NH2, int MODE, int RW>
 static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {

@@ -87,6 +87,7 @@ struct FusedArgs {
     float* partials;         // [gridDim.x][10240 (rgb width 64) / 25600 (128)] per-CTA weight gradients
     int32_t* overflow;
     long long* dbg;          // optional phase timestamps (tools only)
+    unsigned int* sched;     // forward kernel: dynamic tile scheduler slot {next tile, leavers} (set by the launcher), nullptr = static stride
 };
 bool fused_field_supported(const mfn_field_cfg* c);
 size_t fused_blob_bytes(int64_t n_max);

@@ -9,6 +9,7 @@
 // Algorithmic bytes: 60 B/ray + 32 B/sample (+ 8 B/sample stash write+read, + C*G^3/8 B of bitfield).
 #include "march.cuh"
 #include "../../include/mfnerf_b200.h"
+#include <stdlib.h>
 
 namespace mfn {
 
@@ -16,23 +17,32 @@ constexpr int kMarchWarpsPerCta = 8;     // march_write: one warp per ray
 constexpr int kCountThreads = 128;
 constexpr int kWsHeader = 256;           // workspace: [header: u64 @8 total samples | u64 @16 call counter][counts][stash]
 
-// one warp per ray (march.cuh: march_ray_warp)
+// one warp per ray (march.cuh: march_ray_warp_fast, and march_ray_warp for the few rays whose visit order cannot be proven)
 template <bool ONE_CASCADE, bool CONST_DT>
 __global__ void __launch_bounds__(kCountThreads)
 march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ hits_t,
                         const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale, float esf,
-                        const float* __restrict__ noise, int max_samples, int64_t n_rays, int32_t* __restrict__ counts, float2* __restrict__ stash) {
+                        const float* __restrict__ noise, int max_samples, int64_t n_rays, int32_t* __restrict__ counts, float2* __restrict__ stash,
+                        int fast, unsigned long long* __restrict__ header) {
+    __shared__ uint32_t lut[1024];
+    morton_lut_fill(lut, grid_size, threadIdx.x, kCountThreads);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * (kCountThreads / 32) + (threadIdx.x >> 5);
     if (r >= n_rays) return;
-    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
+    MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, scale);
+    c.lut = lut;
     const RayConst q = make_ray(rays_o, rays_d, r);
     float t1 = hits_t[2 * r];
     const float t2 = hits_t[2 * r + 1];
     if (t1 >= 0.0f) t1 = __fmaf_rn(march_dt(t1, c), noise[r], t1);  // only the first sample is jittered (l.195-198)
     float2* my = stash + r * (int64_t)max_samples;
-    const int n = march_ray_warp<ONE_CASCADE, CONST_DT>(t1, t2, max_samples, q, c, bitfield, lane,
-                                                        [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); });
+    auto emit = [&](int rank, float t, float dt) { my[rank] = make_float2(t, dt); };
+    int n = fast ? march_ray_warp_fast<ONE_CASCADE, CONST_DT, true>(t1, t2, max_samples, q, c, bitfield, lane, emit) : -1;
+    if (n < 0) {      // exact replay of the reference's visit order (overwrites whatever the fast attempt stashed)
+        if (fast && lane == 0) atomicAdd(header + 3, 1ull);      // statistics: rays re-marched
+        n = march_ray_warp<ONE_CASCADE, CONST_DT>(t1, t2, max_samples, q, c, bitfield, lane, emit);
+    }
     if (lane == 0) counts[r] = n;
 }
 
@@ -220,8 +230,10 @@ static int march_count_impl(const float* rays_o, const float* rays_d, const floa
         ProfScope ps("march_count", st);
         const unsigned wb = (unsigned)ceil_div(n_rays, kCountThreads / 32);
         const bool one = cascades == 1, cdt = exp_step_factor == 0.0f;
+        const char* fenv = getenv("MFN_MARCH_FAST");      // "0": exact replay for every ray (A/B runs, tests); read per call so that a test can flip it
+        const int fast = !(fenv && fenv[0] == '0');
 #define MFN_MW(A, B) march_count_warp_kernel<A, B><<<wb, kCountThreads, 0, st>>>(rays_o, rays_d, hits_t, bitfield, cascades, grid_size, scale, exp_step_factor, \
-                                                                                noise, max_samples, n_rays, counts, stash)
+                                                                                noise, max_samples, n_rays, counts, stash, fast, (unsigned long long*)workspace)
         if (one && cdt) MFN_MW(true, true); else if (one) MFN_MW(true, false); else if (cdt) MFN_MW(false, true); else MFN_MW(false, false);
 #undef MFN_MW
     }

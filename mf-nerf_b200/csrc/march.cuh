@@ -25,7 +25,13 @@ struct MarchConst {
     float bound0, bound0_inv; // mip 0: min(2^-1, scale) and its reciprocal
     int cascades, grid_size;
     uint32_t g3;
+    const uint32_t* lut;      // optional shared-memory table: lut[v] = v's bits spread to every third position (morton_lut_fill)
 };
+
+// 10-bit coordinate -> its bits at positions 0, 3, 6, ...: three shared-memory loads replace ~24 integer instructions per probe
+__device__ __forceinline__ void morton_lut_fill(uint32_t* lut, int grid_size, int tid, int nthreads) {
+    for (int v = tid; v < grid_size; v += nthreads) lut[v] = spread3_mul((uint32_t)v);
+}
 
 // `dt_scale` is `scale` for the train marcher and (float)cascades for the test marcher -- the reference
 // passes `cascades` to calc_dt in raymarching_test_kernel (raymarching.cu:370,399), a quirk we keep.
@@ -43,6 +49,7 @@ __device__ __forceinline__ MarchConst make_march_const(int cascades, int grid_si
     c.cascades = cascades;
     c.grid_size = grid_size;
     c.g3 = (uint32_t)grid_size * grid_size * grid_size;
+    c.lut = nullptr;
     return c;
 }
 
@@ -72,7 +79,7 @@ struct Probe {
 // the ray leaves the cell.  (ref: raymarching.cu:205-228)
 // ONE_CASCADE: cascades == 1 makes mip = clamp(.., 0, 0) = 0 whatever the position, so the two frexpf and the division are
 // hoisted into MarchConst (bound0 = min(2^-1, scale), bound0_inv = 1/bound0 -- the same IEEE operations, evaluated once).
-template <bool ONE_CASCADE = false>
+template <bool ONE_CASCADE = false, bool LUT = false>
 __device__ __forceinline__ Probe probe_cell(float t, const RayConst& q, const MarchConst& c, const uint8_t* __restrict__ bitfield) {
     Probe p;
     p.x = __fmaf_rn(q.dx, t, q.ox); p.y = __fmaf_rn(q.dy, t, q.oy); p.z = __fmaf_rn(q.dz, t, q.oz);
@@ -95,7 +102,8 @@ __device__ __forceinline__ Probe probe_cell(float t, const RayConst& q, const Ma
     const int nx = (int)fmaxf(0.0f, fminf(fx, c.gsm1));
     const int ny = (int)fmaxf(0.0f, fminf(fy, c.gsm1));
     const int nz = (int)fmaxf(0.0f, fminf(fz, c.gsm1));
-    const uint32_t idx = (uint32_t)mip * c.g3 + morton_encode((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const uint32_t code = LUT ? (c.lut[nx] | (c.lut[ny] << 1) | (c.lut[nz] << 2)) : morton_encode((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+    const uint32_t idx = (uint32_t)mip * c.g3 + code;
     p.occ = (__ldg(bitfield + (idx >> 3)) >> (idx & 7u)) & 1u;
     const float ax = __fmaf_rn(q.sx, 0.5f, __fadd_rn((float)nx, 0.5f));
     const float ay = __fmaf_rn(q.sy, 0.5f, __fadd_rn((float)ny, 0.5f));
@@ -205,6 +213,86 @@ __device__ __forceinline__ int march_ray_warp(float t_start, float t2, int max_e
             const int keep = max_emit - n;
             if (cnt > keep) {
                 uint32_t m = take;  // drop the lowest keep-1 set bits; what is left starts at the keep-th one
+                for (int i = 1; i < keep; ++i) m &= m - 1;
+                const int last = __ffs(m) - 1;
+                take &= (last >= 31) ? FULL : ((1u << (last + 1)) - 1u);
+                cnt = keep;
+            }
+            finished = true;
+        }
+        if ((take >> lane) & 1u) emit(n + __popc(take & ((1u << lane) - 1u)), my_t, p.dt);
+        n += cnt;
+        if (finished) break;
+        t_base = t_next_base;
+    }
+    return n;
+}
+
+// Fast path of the warp marcher: same lattice, same probes, but NO replay of the visit order.  In exact arithmetic every lattice
+// point of an occupied cell is visited (an empty cell's skip lands on the first point behind its exit); in fp32 the one thing
+// that can go wrong is a skip target that overshoots the first point of the next occupied run.  So the warp only PROVES that this
+// did not happen: for every occupied point j whose predecessor is not occupied (a run start), every empty point i since the last
+// visited occupied point (or the ray start) has t_target(i) <= t_j.  Then the chain, which starts at a visited point (the ray's
+// first point, or the successor of a visited occupied point), can only land at or before j, lands on empty points until it
+// reaches j, and advances by at least one point per hop: j is visited, and by induction every occupied point is taken.
+// `carry` is the running maximum of t_target over the empty points of the current gap (as ordered bits: t_target >= t >= 0).
+// Returns the number of samples, or -1 when one run start could not be proven: the caller then re-marches the ray with
+// march_ray_warp (the exact replay).  Expected rate: an exit within an ulp or two of a lattice point, a few rays in 10^3.
+template <bool ONE_CASCADE, bool CONST_DT, bool LUT, typename Emit>
+__device__ __forceinline__ int march_ray_warp_fast(float t_start, float t2, int max_emit, const RayConst& q, const MarchConst& c,
+                                                   const uint8_t* __restrict__ bitfield, int lane, Emit emit) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    int n = 0;
+    float t_base = t_start;
+    uint32_t carry = 0u;
+    while (t_base >= 0.0f && t_base < t2 && n < max_emit) {
+        float my_t, t_next_base;
+        bool closed = false;
+        if (CONST_DT) {
+            const float qstep = __fsub_rn(__fadd_rn(c.dt_min, t_base), t_base);
+            my_t = __fmaf_rn((float)lane, qstep, t_base);
+            const float succ = __fadd_rn(c.dt_min, my_t);
+            const float nxt_c = __shfl_down_sync(FULL, my_t, 1);
+            closed = __all_sync(FULL, lane == 31 || succ == nxt_c);
+            t_next_base = __shfl_sync(FULL, succ, 31);
+        }
+        if (!closed) {
+            float tt = t_base; my_t = t_base;
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                if (j == lane) my_t = tt;
+                tt = march_next(tt, c);
+            }
+            t_next_base = tt;
+        }
+        const bool active = my_t < t2;
+        Probe p;
+        p.occ = false; p.t_target = 0.f; p.dt = 0.f;
+        if (active) p = probe_cell<ONE_CASCADE, LUT>(my_t, q, c, bitfield);
+        const uint32_t act_mask = __ballot_sync(FULL, active);
+        const uint32_t occ_mask = __ballot_sync(FULL, active && p.occ);
+        const uint32_t e_bits = (active && !p.occ) ? __float_as_uint(p.t_target) : 0u;
+        uint32_t starts = occ_mask & ~(occ_mask << 1);
+        while (starts) {                                      // (warp-uniform) usually 0 or 1 run start per batch
+            const int j = __ffs(starts) - 1;
+            starts &= starts - 1u;
+            const uint32_t below = occ_mask & ((1u << j) - 1u);
+            const int prev = below ? 31 - __clz(below) : -1;  // last occupied lane in front of j
+            const bool in_gap = lane > prev && lane < j;
+            uint32_t m = __reduce_max_sync(FULL, in_gap ? e_bits : 0u);
+            if (prev < 0) m = max(m, carry);
+            if (m > __shfl_sync(FULL, __float_as_uint(my_t), j)) return -1;
+        }
+        const int last_occ = occ_mask ? 31 - __clz(occ_mask) : -1;
+        const uint32_t trail = __reduce_max_sync(FULL, lane > last_occ ? e_bits : 0u);
+        carry = last_occ < 0 ? max(carry, trail) : trail;
+        uint32_t take = occ_mask;
+        bool finished = act_mask != FULL;                    // a point with t >= t2 exists: the chain ends at or before the next batch
+        int cnt = __popc(take);
+        if (n + cnt >= max_emit) {
+            const int keep = max_emit - n;
+            if (cnt > keep) {
+                uint32_t m = take;
                 for (int i = 1; i < keep; ++i) m &= m - 1;
                 const int last = __ffs(m) - 1;
                 take &= (last >= 31) ? FULL : ((1u << (last + 1)) - 1u);

@@ -148,6 +148,10 @@ class NGPEngine:
         self._comp_scratch = torch.zeros(4, device=d)
         self._n_back = ctypes.c_void_p(_lib.lib.mfn_field_count_ptr(ctypes.byref(self.cfg), ptr(self.field_ws), S)) if self._fused else None
         self._graph = None
+        self._graph_adam = None
+        # one GPU: the next step's marching front waits for the scatter kernel and overlaps the optimiser only (memory-bound, it leaves
+        # the issue slots free) instead of competing with the backward / scatter kernels
+        self._march_after_scatter = os.environ.get("MFN_MARCH_OVERLAP", "back") == "adam"
         self._cells_ws = None
         self.graph_replays = 0
         self.launches_per_forward_backward = 0
@@ -242,40 +246,58 @@ class NGPEngine:
     def update_density_grid(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False, decay=0.95):
         """networks.py:242-271 without its host syncs (nonzero / .item()) and as a handful of fused kernels (csrc/density_grid.cu):
         cells -> jittered positions -> density query -> decay/max update -> mean of the positive cells -> packbits with the threshold
-        min(mean, density_threshold) read on the device.  Occupied cells are drawn with a cumsum + searchsorted instead of nonzero."""
-        d, st = self.dev, stream_ptr(self.dev)
+        min(mean, density_threshold) read on the device.  Occupied cells are drawn with a cumsum + searchsorted instead of nonzero.
+        Two halves: _dg_prepare (which cells, where inside them: needs the occupancy grid only) and _dg_apply (density query with the
+        CURRENT parameters, grid update, bitfield) -- the pipelined step runs the first half while the previous step's backward pass
+        and optimiser are still in flight."""
+        prep = self._dg_prepare(density_threshold, warmup)
         self._wait_comm()
+        self._dg_apply(prep, density_threshold, decay)
+
+    @torch.no_grad()
+    def _dg_prepare(self, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=False):
+        d, st = self.dev, stream_ptr(self.dev)
         G3 = G ** 3
         M = G3 // 4
         if not hasattr(self, "_dg_xyz"):
-            self._dg_xyz = torch.empty(G3, 3, device=d)                      # positions of the queried cells (all cells: G^3, sampled: 2M)
-            self._dg_idx = torch.empty(2 * M, dtype=torch.int32, device=d)
+            self._dg_xyz = [torch.empty(G3, 3, device=d) for _ in range(self.cascades)]     # positions of the queried cells (all cells: G^3, sampled: 2M)
+            self._dg_idx = [torch.empty(2 * M, dtype=torch.int32, device=d) for _ in range(self.cascades)]
             self._dg_sig = torch.empty(G3, device=d)
             self._dg_scratch = torch.zeros(4, device=d)
             self._dg_mean = torch.zeros(1, device=d)
             self._dg_calls = 0
+        plan = []
         for c in range(self.cascades):
             self._dg_calls += 1
             seed = (self._dg_calls * 0x9E3779B97F4A7C15 + 1337) & 0xFFFFFFFFFFFFFFFF     # same sequence on every rank: replicas stay identical
-            grid_c = self.density_grid[c]
+            grid_c, xyz, idx = self.density_grid[c], self._dg_xyz[c], self._dg_idx[c]
             if warmup:                                    # get_all_cells (networks.py:157-168)
                 n, idx_ptr = G3, None
-                call("mfn_grid_cell_positions", None, 0, n, c, self.scale, G, seed, None, ptr(self._dg_xyz), st)
+                call("mfn_grid_cell_positions", None, 0, n, c, self.scale, G, seed, None, ptr(xyz), st)
             else:                                         # sample_uniform_and_occupied_cells (networks.py:170-197)
-                n, idx_ptr = 2 * M, ptr(self._dg_idx)
-                call("mfn_grid_cell_positions", None, 1, M, c, self.scale, G, seed, ptr(self._dg_idx), ptr(self._dg_xyz), st)
+                n, idx_ptr = 2 * M, ptr(idx)
+                call("mfn_grid_cell_positions", None, 1, M, c, self.scale, G, seed, ptr(idx), ptr(xyz), st)
                 cs = torch.cumsum(grid_c > density_threshold, 0, dtype=torch.int32)
-                call("mfn_grid_draw_occupied", ptr(cs), G3, M, seed ^ 0x3333333333333333, ptr(self._dg_idx[M:]), st)
+                call("mfn_grid_draw_occupied", ptr(cs), G3, M, seed ^ 0x3333333333333333, ptr(idx[M:]), st)
                 # morton-sorted cells are spatially coherent: the density query's hash-grid gathers run ~3x faster than on the raw draw
                 # (the update rule does not depend on the order of the cells)
-                self._dg_idx.copy_(torch.sort(self._dg_idx)[0])
-                call("mfn_grid_cell_positions", ptr(self._dg_idx), 0, 2 * M, c, self.scale, G, seed ^ 0x5555555555555555, None, ptr(self._dg_xyz), st)
+                idx.copy_(torch.sort(idx)[0])
+                call("mfn_grid_cell_positions", ptr(idx), 0, 2 * M, c, self.scale, G, seed ^ 0x5555555555555555, None, ptr(xyz), st)
+            plan.append((c, n, idx_ptr))
+        return plan
+
+    @torch.no_grad()
+    def _dg_apply(self, plan, density_threshold=0.01 * MAX_SAMPLES / 3 ** 0.5, decay=0.95):
+        d, st = self.dev, stream_ptr(self.dev)
+        G3 = G ** 3
+        for c, n, idx_ptr in plan:
+            grid_c = self.density_grid[c]
             sig = self._dg_sig[:n]
             need = _lib.lib.mfn_field_workspace_bytes(ctypes.byref(self.cfg), n, 0)
             if getattr(self, "_dg_ws", None) is None or self._dg_ws.numel() < need:      # never the training workspace: the previous
                 self._dg_ws = torch.empty(need, dtype=torch.uint8, device=d)               # step's backward may still be reading it
             ws = self._dg_ws
-            call("mfn_density_fwd", ctypes.byref(self.cfg), ptr(self.xyz_params_h), ptr(self._dg_xyz), n, None, ptr(sig), ptr(ws), ws.numel(), st)
+            call("mfn_density_fwd", ctypes.byref(self.cfg), ptr(self.xyz_params_h), ptr(self._dg_xyz[c]), n, None, ptr(sig), ptr(ws), ws.numel(), st)
             call("mfn_grid_update", ptr(grid_c), idx_ptr, ptr(sig), G3, n, float(decay), st)
         call("mfn_grid_mean_positive", ptr(self.density_grid), self.density_grid.numel(), ptr(self._dg_scratch), ptr(self._dg_mean), st)
         self._mean_density = self._dg_mean
@@ -416,9 +438,14 @@ class NGPEngine:
                 self._march()
             with torch.cuda.graph(gb):
                 self._field_front()
+            self._graph_adam = None
             with torch.cuda.graph(gc):
                 self._field_back()
-                if not self.collectives:      # one GPU: the optimiser is the last node of the back graph (its scalars come from device memory)
+                if not self.collectives and not self._march_after_scatter:      # one GPU: the optimiser is the last node of the back graph (its scalars come from device memory)
+                    self._adam_from_device_scalars(stream_ptr(self.dev))
+            if not self.collectives and self._march_after_scatter:              # ... or a graph of its own, so that the next step's march can start between the two
+                self._graph_adam = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_adam):
                     self._adam_from_device_scalars(stream_ptr(self.dev))
             self._graph_march, self._graph, self._graph_back = ga, gb, gc
             self._graph_back_only = gc
@@ -428,7 +455,7 @@ class NGPEngine:
                 self._forward_backward()
             self._graph = g
         self.launches_per_forward_backward = int(_lib.lib.mfn_launch_count() - l0)
-        if self.dp and not self.collectives:      # the backward pass alone, without the optimiser node (replay_forward_backward)
+        if self.dp and not self.collectives and not self._march_after_scatter:      # the backward pass alone, without the optimiser node (replay_forward_backward)
             gd = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gd):
                 self._field_back()
@@ -614,7 +641,7 @@ class NGPEngine:
         main = torch.cuda.current_stream(self.dev)
         ms, cs = self._march_stream, self._comm_stream
         ms.wait_stream(main)         # everything enqueued on the main stream so far: step t-1's field front, and whatever the caller did
-        if self.collectives and self._back_pending:
+        if (self.collectives or self._march_after_scatter) and self._back_pending:
             # data-parallel: the gradient exchange leaves the SMs mostly idle, so the marching front is better spent overlapping IT
             # than competing with the backward / scatter kernels for issue slots (measured on 8 GPUs: 0.478 vs 0.507 ms/step)
             ms.wait_event(self._back_done)
@@ -622,9 +649,10 @@ class NGPEngine:
         with torch.cuda.stream(ms):
             if not self._deep:
                 self._wait_comm()    # unfused field shapes: the backward still reads the sample arrays
-            if global_step % 16 == 0:                    # the occupancy update queries the field: needs the updated parameters
+            if global_step % 16 == 0:                    # the occupancy update queries the field: needs the updated parameters --
+                plan = self._dg_prepare(warmup=global_step < 256)      # -- but choosing the cells does not: overlaps the previous step's back stage
                 self._wait_comm()
-                self.update_density_grid(warmup=global_step < 256)
+                self._dg_apply(plan)
             copy_batch()
             if self._graph is not None:
                 self._graph_march.replay()
@@ -648,9 +676,14 @@ class NGPEngine:
         with torch.cuda.stream(cs):
             if self._graph is not None:
                 self._graph_back.replay()          # one GPU: ends with the optimiser (whole vector, gradient buffer zeroed by it)
+                if self._graph_adam is not None:
+                    self._back_done.record(cs); self._back_pending = True
+                    self._graph_adam.replay()
             else:
                 self._field_back()
                 if not self.collectives:
+                    if self._march_after_scatter:
+                        self._back_done.record(cs); self._back_pending = True
                     self._adam_from_device_scalars(self._comm_stream_ptr)
             if self.collectives and self._symm is not None:
                 # ONE kernel: sum this rank's shard of every rank's gradients through the NVSwitch, clear it everywhere, Adam on the fp32

@@ -376,8 +376,8 @@ def test_update_density_grid_fused_kernels_follow_the_reference_rule():
         eng.update_density_grid(warmup=warm)
         torch.cuda.synchronize()
         n = G3 if warm else G3 // 2
-        xyz = eng._dg_xyz[:n].clone()
-        idx = torch.arange(G3, device="cuda") if warm else eng._dg_idx[:n].long()
+        xyz = eng._dg_xyz[0][:n].clone()
+        idx = torch.arange(G3, device="cuda") if warm else eng._dg_idx[0][:n].long()
         # (a) position -> cell: the inverse of xyzs_w = (coords / (G-1) * 2 - 1) * (s - half) +- half
         s, half = 0.5, 0.5 / G
         cell = torch.round(((xyz / (s - half)) + 1) / 2 * (G - 1))     # jitter is < half a cell spacing of this lattice

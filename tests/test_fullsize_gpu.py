@@ -178,3 +178,31 @@ def test_render_full_frame_wavefront_equals_per_op_loop():
         torch.testing.assert_close(c[k], b[k], rtol=0, atol=1e-6)
     assert c["iterations"] < a["iterations"]
     assert float(a["opacity"].min()) >= 0 and float(a["opacity"].max()) <= 1 + 1e-5
+
+
+@pytest.mark.parametrize("name,n_rays", [("lego", 65536), ("full", 8192), ("unbounded", 32768), ("axis", 8192)])
+def test_fast_marcher_equals_the_exact_replay(name, n_rays, monkeypatch):
+    """march.cuh: march_ray_warp_fast takes every occupied lattice point after PROVING that the reference's sequential visit order
+    cannot have skipped one, and hands the ray to the exact replay (march_ray_warp) when the proof fails.  Both must give the same
+    bits; the number of re-marched rays is read from the workspace header."""
+    import vren
+    sc = scenes.scene(name, n_rays, seed=11)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    o, d, bits = T(sc["rays_o"]), T(sc["rays_d"]), T(sc["bitfield"])
+    _, ht, _ = vren.ray_aabb_intersect(o, d, T(sc["center"]), T(sc["half"]), 1)
+    h = T(scenes.near_clamp(ht.cpu().numpy()))
+    args = (o, d, h, bits, sc["cascades"], sc["scale"], sc["esf"], T(sc["noise"]), 128, 1024)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MFN_MARCH_FAST", mode)
+        vren.raymarching_train(*args)                       # (allocates / sizes the shim's workspace)
+        ws = vren._ws_cache[torch.cuda.current_device()]
+        ws[:256].zero_()
+        out[mode] = vren.raymarching_train(*args)
+        torch.cuda.synchronize()
+        out[mode + "_remarched"] = int(ws[:256].view(torch.int64)[3])
+    assert out["0_remarched"] == 0
+    for a, b in zip(out["0"], out["1"]):
+        assert a.shape == b.shape and torch.equal(a, b)
+    print(f"{name}: {int(out['1'][5][0])} samples, {out['1_remarched']} of {n_rays} rays re-marched by the exact replay")
+    assert out["1_remarched"] < n_rays // 20

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "mf-nerf_b200")):
     sys.path.insert(0, p)
 import torch
-dbg = torch.zeros(256 + 6 * 40, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(1024 + 4 * 4096, dtype=torch.int64, device="cuda")
 os.environ["MFN_FWD_DBG"] = str(dbg.data_ptr())
 import bench
 from mfnerf_b200 import synthetic as syn
@@ -25,6 +25,20 @@ for k in range(12):
     if r[8] == 0: continue
     d = [int(r[j] - r[j - 1]) for j in range(1, 9)]
     print(f"tile {k:2d}: total {int(r[8]-r[0]):7d} | " + " ".join(f"{names[j]}={d[j-1]}" for j in range(1, 9)) + f" | t255 gather={int(r[9]-r[0])}")
+
+import numpy as np
+e = dbg.cpu()[1024:].view(-1, 4).numpy()
+e = e[e[:, 1] > 0]
+t0 = e[:, 0].min()
+dur = (e[:, 1] - e[:, 0]) / 1e3
+print(f"forward kernel, {len(e)} CTAs: entry {((e[:,0]-t0)/1e3).min():.1f}..{((e[:,0]-t0)/1e3).max():.1f} us, exit {((e[:,1]-t0)/1e3).min():.1f}..{((e[:,1]-t0)/1e3).max():.1f} us, "
+      f"CTA duration min {dur.min():.1f} mean {dur.mean():.1f} max {dur.max():.1f} us")
+per_tile = dur / np.maximum(e[:, 3], 1)
+sm = e[:, 2]
+by_sm = np.array([per_tile[sm == k].mean() for k in np.unique(sm)])
+print("  us per tile by SM (sorted):", " ".join(f"{v:.1f}" for v in np.sort(by_sm)[::8]))
+print("  exit time by SM (sorted):", " ".join(f"{v:.0f}" for v in np.sort(np.array([((e[:,1]-t0)/1e3)[sm == k].max() for k in np.unique(sm)]))[::8]))
+print("samples of the last step", int(eng.counter[0].item()))
 
 # backward kernel: stamps after every MMA-completion wait ("w") and every barrier ("s") of CTA 0 / thread 0
 b = dbg.cpu()[256:].view(6, 40).numpy()
