@@ -243,7 +243,9 @@ __host__ __device__ constexpr uint32_t kstep_mnmajor(int C) { return 2u * (uint3
 
 // ------------------------------------------------------------------------------------------------------------------ forward
 // MODE 0: inference (sigma + rgb), 1: training (also saves X tile, direction, fp16 rgb and normalised position), 2: density only (sigma),
-// 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107).
+// 3: the 16 raw outputs of the grid + sigma MLP in fp16 (tcnn.NetworkWithInputEncoding's forward, networks.py:107),
+// 4: inference inside the render wavefront (render.cu): row i = sample i % N_samples of alive slot i / N_samples; x = o + t d and the
+//    direction come from the ray (the marcher stores t and dt only: 8 B instead of 32 B per row), rows past N_eff are skipped.
 // 256 threads: thread t works on sample row t % 128 (= its TMEM lane); the two threads of a row split the 16 grid levels in the
 // gather phase and the accumulator columns in the hidden-layer epilogues.
 // scheduler slots: {next tile, CTAs that have left}; zero at module load and zero again after every launch (the last leaver resets)
@@ -272,7 +274,7 @@ template <int NH2, int MODE, bool MIXED, int RW>
 __global__ void __launch_bounds__(kFwdThreads, Lay<RW>::FwdCtas)
 field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constant__ GridMeta m) {
     using L = Lay<RW>;
-    constexpr bool TRAIN = (MODE == 1), RGB = (MODE < 2);
+    constexpr bool TRAIN = (MODE == 1), RAYS = (MODE == 4), RGB = (MODE < 2) || RAYS;
     // No tile is alive across stages, so X, H1, CAT, H2 and H3 share ONE tile region and the 16-column output accumulator shares
     // the hidden accumulator's TMEM columns (the gather is bound by resident parallelism: every KiB counts).  In training mode the
     // X tile leaves with a bulk async store that is waited for (its shared-memory read) before H1 overwrites the region.
@@ -312,10 +314,25 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
     const uint32_t* table = reinterpret_cast<const uint32_t*>(a.table);
     const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
 
+    // render mode: N_samples of this iteration (uniform) and the magic multiplier of the division row -> alive slot
+    // (exact for rows < 2^26 and N_samples <= 64: the error of umulhi(i, ceil(2^32 / ns)) stays below 1 / 64)
+    uint32_t r_ns = 1u, r_magic = 0u;
+    const int32_t* r_alive = nullptr;
+    if (RAYS) {
+        r_ns = (uint32_t)max(a.ray_plan[3], 1);
+        r_magic = (uint32_t)((0x100000000ull + r_ns - 1u) / r_ns);
+        r_alive = a.ray_alive_lists + (size_t)a.ray_plan[2] * a.ray_list_stride;
+    }
     int tile_no = 0;
     for (int64_t tile = next_tile_s; tile < n_tiles; tile = next_tile_s, ++tile_no) {
         const int64_t i = tile * kFT + row;
-        const bool valid = i < n;
+        bool valid = i < n;
+        int ray_of_row = 0;
+        if (RAYS && valid) {
+            const uint32_t slot = r_ns == 1u ? (uint32_t)i : __umulhi((uint32_t)i, r_magic);
+            valid = (int)((uint32_t)i - slot * r_ns) < a.ray_n_eff[slot];
+            ray_of_row = r_alive[slot];
+        }
         int tile_after = (int)tile + (int)gridDim.x;
         if (a.sched && tid == 0) tile_after = (int)atomicAdd(a.sched, 1u);    // consumed at the end of this tile
         MFN_TS(0);
@@ -323,10 +340,20 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         {
             const int grow = tid >> 1, xb = tid & 1;
             const int64_t gi = tile * kFT + grow;
-            const bool gvalid = gi < n;
+            bool gvalid = gi < n;
             float x = 0.5f, y = 0.5f, z = 0.5f;
+            if (RAYS && gvalid) {
+                const uint32_t slot = r_ns == 1u ? (uint32_t)gi : __umulhi((uint32_t)gi, r_magic);
+                gvalid = (int)((uint32_t)gi - slot * r_ns) < a.ray_n_eff[slot];
+                if (gvalid) {      // the marcher's own expression (march.cuh: probe_cell), bit for bit
+                    const int r = r_alive[slot];
+                    const float t = a.ray_ts[gi];
+                    x = __fmaf_rn(a.rays_d[3 * r], t, a.rays_o[3 * r]); y = __fmaf_rn(a.rays_d[3 * r + 1], t, a.rays_o[3 * r + 1]);
+                    z = __fmaf_rn(a.rays_d[3 * r + 2], t, a.rays_o[3 * r + 2]);
+                }
+            }
             if (gvalid) {
-                x = a.xyzs[3 * gi]; y = a.xyzs[3 * gi + 1]; z = a.xyzs[3 * gi + 2];
+                if (!RAYS) { x = a.xyzs[3 * gi]; y = a.xyzs[3 * gi + 1]; z = a.xyzs[3 * gi + 2]; }
                 x = __fdiv_rn(__fsub_rn(x, a.mn[0]), __fsub_rn(a.mx[0], a.mn[0]));      // networks.py:105
                 y = __fdiv_rn(__fsub_rn(y, a.mn[1]), __fsub_rn(a.mx[1], a.mn[1]));
                 z = __fdiv_rn(__fsub_rn(z, a.mn[2]), __fsub_rn(a.mx[2], a.mn[2]));
@@ -335,6 +362,10 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
             // feature pair of level l = columns 2l, 2l+1 of row `grow`: core matrix l / 4, byte 4 * (l % 4) of the row's 16-byte chunk;
             // lane xb of the pair stores the levels of its parity
             unsigned char* xrow = smem + oT + tile_off(grow, 0, 32) + 4 * xb;
+            if (RAYS && !__any_sync(0xffffffffu, gvalid)) {      // 16 padding rows: nothing to gather
+#pragma unroll
+                for (int l = 0; l < 16; l += 2) *reinterpret_cast<uint32_t*>(xrow + (l >> 2) * 128 + (l & 2) * 4) = 0u;
+            } else
 #pragma unroll 2
             for (int l = 0; l < 16; l += 2) {
                 uint32_t v0, v1;
@@ -363,7 +394,10 @@ field_fwd_fused_kernel(const __grid_constant__ FusedArgs a, const __grid_constan
         // the view direction of this row (partner thread), requested now so that the layer-1 MMA wait hides its latency: a load issued
         // just before a stage boundary is waited for by the boundary's proxy fence
         float dirx = 0.f, diry = 0.f, dirz = 1.f;
-        if (RGB && hsel == 1 && valid) { dirx = a.dirs[3 * i]; diry = a.dirs[3 * i + 1]; dirz = a.dirs[3 * i + 2]; }
+        if (RGB && hsel == 1 && valid) {
+            const float* dp = RAYS ? a.rays_d + 3 * (size_t)ray_of_row : a.dirs + 3 * i;
+            dirx = dp[0]; diry = dp[1]; dirz = dp[2];
+        }
         // ---- layer 1: H1 = relu(X . W1^T)
         if (tid == 0) {
             tc_fence_after();
@@ -841,7 +875,7 @@ static void launch_fwd_m(const FusedArgs& a, const GridMeta& m, cudaStream_t st)
     static const bool dynamic = !(getenv("MFN_FWD_STATIC") && atoi(getenv("MFN_FWD_STATIC")));
     if (!sched_base) { void* p = nullptr; if (cudaGetSymbolAddress(&p, g_tile_sched) == cudaSuccess) sched_base = (unsigned int*)p; }
     FusedArgs b = a;
-    b.sched = (dynamic && sched_base) ? sched_base + 2 * (MODE * 16 + (seq.fetch_add(1) & 15u)) : nullptr;
+    b.sched = (dynamic && sched_base) ? sched_base + 2 * ((MODE & 3) * 16 + (seq.fetch_add(1) & 15u)) : nullptr;
     field_fwd_fused_kernel<NH2, MODE, MIXED, RW><<<(unsigned)(tiles < cap ? tiles : cap), kFwdThreads, smem_bytes, st>>>(b, m);
 }
 template <int NH2, int MODE, int RW>
@@ -850,10 +884,10 @@ static void launch_fwd(const FusedArgs& a, const GridMeta& m, cudaStream_t st) {
 }
 template <int NH2, int RW>
 static void launch_fwd_mode(const FusedArgs& a, const GridMeta& m, int mode, cudaStream_t st) {
-    if (mode == 0) launch_fwd<NH2, 0, RW>(a, m, st); else launch_fwd<NH2, 1, RW>(a, m, st);
+    if (mode == 0) launch_fwd<NH2, 0, RW>(a, m, st); else if (mode == 4) launch_fwd<NH2, 4, RW>(a, m, st); else launch_fwd<NH2, 1, RW>(a, m, st);
 }
 
-// mode: 0 inference, 1 training, 2 density only, 3 raw 16 outputs of the sigma network
+// mode: 0 inference, 1 training, 2 density only, 3 raw 16 outputs of the sigma network, 4 inference inside the render wavefront
 int fused_field_forward(const FusedArgs& a, const GridMeta& m, int rgb_width, int rgb_hidden, int mode, cudaStream_t st) {
     ProfScope ps(mode >= 2 ? "density_fwd" : "field_fwd", st);
     if (mode == 3) { launch_fwd<1, 3, 64>(a, m, st); return check_launch("mfn_geo_fwd(fused)", st); }      // (the sigma network only: the rgb width does not matter)

@@ -87,6 +87,11 @@ struct FusedArgs {
     float* partials;         // [gridDim.x][10240 (rgb width 64) / 25600 (128)] per-CTA weight gradients
     int32_t* overflow;
     long long* dbg;          // optional phase timestamps (tools only)
+    // render wavefront (forward MODE 4): rows are (alive slot, sample) pairs; position and direction are derived from the ray and the
+    // sample's t instead of being read from per-row arrays, and rows past a ray's N_eff are skipped (the reference evaluates
+    // xyzs[valid_mask] only, rendering.py:83-92)
+    const float* ray_ts; const float* rays_o; const float* rays_d; const int32_t* ray_plan; const int32_t* ray_alive_lists; const int32_t* ray_n_eff;
+    int ray_list_stride;
     unsigned int* sched;     // forward kernel: dynamic tile scheduler slot {next tile, leavers} (set by the launcher), nullptr = static stride
 };
 bool fused_field_supported(const mfn_field_cfg* c);

@@ -310,13 +310,13 @@ __device__ __forceinline__ int march_ray_warp_fast(float t_start, float t2, int 
 
 // Sequential marcher (one thread per ray) -- the reference's own control flow; used by the test-time
 // marcher where each call only asks for a handful of samples per ray.
-template <typename Emit>
+template <bool ONE_CASCADE = false, bool LUT = false, typename Emit>
 __device__ __forceinline__ int march_ray_thread(float t, float t2, int max_emit, const RayConst& q, const MarchConst& c,
                                                 const uint8_t* __restrict__ bitfield, Emit emit, float* t_after) {
     int s = 0;
     float t_last = t;
     while (t < t2 && s < max_emit) {
-        const Probe p = probe_cell<false>(t, q, c, bitfield);
+        const Probe p = probe_cell<ONE_CASCADE, LUT>(t, q, c, bitfield);
         if (p.occ) {
             emit(s, t, p.dt, p.x, p.y, p.z);
             t = __fadd_rn(p.dt, t);

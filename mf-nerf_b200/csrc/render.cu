@@ -76,35 +76,30 @@ __global__ void render_plan_kernel(RenderPlan* __restrict__ plan, int n_rays, in
     render_make_plan(plan, n_rays, min_samples, max_samples, cap_rows);
 }
 
+template <bool ONE_CASCADE>
 __global__ void __launch_bounds__(128)
 render_march_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float* __restrict__ hits_t, const int32_t* __restrict__ alive_lists,
                     int list_stride, const RenderPlan* __restrict__ plan, const uint8_t* __restrict__ bitfield, int cascades, int grid_size, float scale,
-                    float esf, int max_samples, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas, float* __restrict__ ts,
-                    int32_t* __restrict__ n_eff) {
+                    float esf, int max_samples, float* __restrict__ deltas, float* __restrict__ ts, int32_t* __restrict__ n_eff) {
     const int cur = plan->cur, na = plan->n_alive[cur], ns = plan->n_samples;
+    if ((int)(blockIdx.x * blockDim.x) >= na) return;
+    __shared__ uint32_t lut[1024];
+    morton_lut_fill(lut, grid_size, threadIdx.x, 128);
+    __syncthreads();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= na) return;
     const int r = alive_lists[cur * list_stride + n];
-    const MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, (float)cascades);   // the test marcher's calc_dt quirk
+    MarchConst c = make_march_const(cascades, grid_size, scale, esf, max_samples, (float)cascades);   // the test marcher's calc_dt quirk
+    c.lut = lut;
     const RayConst q = make_ray(rays_o, rays_d, r);
     const float t = hits_t[2 * r], t2 = hits_t[2 * r + 1];
-    float* px = xyzs + (size_t)n * ns * 3;
-    float* pd = dirs + (size_t)n * ns * 3;
+    // only t and dt of a sample are stored (8 B per row): the field kernel derives x = o + t d and the direction from the ray, and
+    // neither it nor the compositor looks at rows past N_eff -- no padding is written
     float* pdt = deltas + (size_t)n * ns;
     float* pt = ts + (size_t)n * ns;
     float t_after;
-    const int s = march_ray_thread(t, t2, ns, q, c, bitfield,
-                                   [&](int k, float tk, float dt, float x, float y, float z) {
-                                       px[3 * k] = x; px[3 * k + 1] = y; px[3 * k + 2] = z;
-                                       pd[3 * k] = q.dx; pd[3 * k + 1] = q.dy; pd[3 * k + 2] = q.dz;
-                                       pt[k] = tk; pdt[k] = dt;
-                                   }, &t_after);
+    const int s = march_ray_thread<ONE_CASCADE, true>(t, t2, ns, q, c, bitfield, [&](int k, float tk, float dt, float, float, float) { pt[k] = tk; pdt[k] = dt; }, &t_after);
     if (s > 0) hits_t[2 * r] = t_after;
-    for (int k = s; k < ns; ++k) {      // padding rows: evaluated by the field kernel, ignored by the compositor (finite inputs)
-        px[3 * k] = 0.f; px[3 * k + 1] = 0.f; px[3 * k + 2] = 0.f;
-        pd[3 * k] = q.dx; pd[3 * k + 1] = q.dy; pd[3 * k + 2] = q.dz;
-        pt[k] = 0.f; pdt[k] = 0.f;
-    }
     n_eff[n] = s;
 }
 
@@ -177,7 +172,7 @@ __global__ void render_finish_kernel(float* __restrict__ rgb, const float* __res
     rgb[3 * r] += bg_r * k; rgb[3 * r + 1] += bg_g * k; rgb[3 * r + 2] += bg_b * k;
 }
 
-struct RenderWs { size_t plan, hits, alive, neff, xyzs, dirs, deltas, ts, sigmas, rgbs, total; int64_t cap_rows; };
+struct RenderWs { size_t plan, hits, alive, neff, deltas, ts, sigmas, rgbs, total; int64_t cap_rows; };
 static RenderWs render_ws(int64_t n_rays, int min_samples) {
     RenderWs w{};
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
@@ -187,8 +182,6 @@ static RenderWs render_ws(int64_t n_rays, int min_samples) {
     w.hits = o; o += al(n_rays * 8);
     w.alive = o; o += al(n_rays * 4) * 2;
     w.neff = o; o += al(n_rays * 4);
-    w.xyzs = o; o += al(cap * 12);
-    w.dirs = o; o += al(cap * 12);
     w.deltas = o; o += al(cap * 4);
     w.ts = o; o += al(cap * 4);
     w.sigmas = o; o += al(cap * 4);
@@ -247,16 +240,18 @@ extern "C" int mfn_render_iterations(const mfn_field_cfg* cfg, const void* xyz_p
     const int list_stride = (int)(((n_rays * 4 + 255) / 256 * 256) / 4);
     const unsigned ray_blocks = (unsigned)ceil_div(n_rays, 128);
     FusedArgs f{};
-    f.xyzs = (const float*)(ws + w.xyzs); f.dirs = (const float*)(ws + w.dirs); f.n_max = w.cap_rows; f.n_dev = &plan->n_rows;
+    f.n_max = w.cap_rows; f.n_dev = &plan->n_rows;
+    f.ray_ts = (const float*)(ws + w.ts); f.rays_o = rays_o; f.rays_d = rays_d; f.ray_plan = (const int32_t*)plan; f.ray_alive_lists = (const int32_t*)(ws + w.alive);
+    f.ray_n_eff = (const int32_t*)(ws + w.neff); f.ray_list_stride = list_stride;
     for (int k = 0; k < 3; ++k) { f.mn[k] = cfg->xyz_min[k]; f.mx[k] = cfg->xyz_max[k]; }
     f.w_sigma = (const __half*)xyz_params_h; f.table = f.w_sigma + 64 * 32 + 16 * 64; f.w_rgb = (const __half*)rgb_params_h; f.rgb_act = cfg->rgb_act;
     f.sigmas = (float*)(ws + w.sigmas); f.rgbs = (float*)(ws + w.rgbs);
     for (int it = 0; it < n_iterations; ++it) {
-        render_march_kernel<<<ray_blocks, 128, 0, st>>>(rays_o, rays_d, (float*)(ws + w.hits), (const int32_t*)(ws + w.alive), list_stride, plan, density_bitfield,
-                                                        cascades, grid_size, scale, exp_step_factor, max_samples, (float*)(ws + w.xyzs), (float*)(ws + w.dirs),
-                                                        (float*)(ws + w.deltas), (float*)(ws + w.ts), (int32_t*)(ws + w.neff));
+        (cascades == 1 ? render_march_kernel<true> : render_march_kernel<false>)<<<ray_blocks, 128, 0, st>>>(rays_o, rays_d, (float*)(ws + w.hits), (const int32_t*)(ws + w.alive), list_stride, plan, density_bitfield,
+                                                        cascades, grid_size, scale, exp_step_factor, max_samples, (float*)(ws + w.deltas), (float*)(ws + w.ts),
+                                                        (int32_t*)(ws + w.neff));
         note_launch(1);
-        if ((rc = fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, 0, st)) != MFN_OK) return rc;
+        if ((rc = fused_field_forward(f, m, cfg->rgb_width, cfg->rgb_hidden, 4, st)) != MFN_OK) return rc;
         render_composite_kernel<<<ray_blocks, 128, 0, st>>>((const float*)(ws + w.sigmas), (const float*)(ws + w.rgbs), (const float*)(ws + w.deltas),
                                                             (const float*)(ws + w.ts), (int32_t*)(ws + w.alive), list_stride, plan, T_threshold,
                                                             (const int32_t*)(ws + w.neff), opacity, depth, rgb, (int)n_rays, min_samples, max_samples,

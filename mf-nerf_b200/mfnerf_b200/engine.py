@@ -558,14 +558,14 @@ class NGPEngine:
         self._sl_ph = self.params_h[sl]
         self._adam_ptrs = (ptr(self.params[sl]), ptr(self._grad_shard if self.collectives else self.grads), ptr(self.exp_avg[sl]), ptr(self.exp_avg_sq[sl]),
                            ptr(self.params_h[sl]))
-        self._march_stream = torch.cuda.Stream(self.dev)
+        self._march_stream = torch.cuda.Stream(self.dev, priority=int(os.environ.get("MFN_MARCH_PRIO", "0")))
         self._march_done = torch.cuda.Event()
         self._cb_done = torch.cuda.Event()
         self._back_done = torch.cuda.Event()
         self._back_pending = False
         # high priority: the back stream (field backward, scatter, Adam) is the step's critical path; the marching front that overlaps it
         # (default priority) only gets the issue slots it leaves free
-        self._comm_stream = torch.cuda.Stream(self.dev, priority=-1)
+        self._comm_stream = torch.cuda.Stream(self.dev, priority=int(os.environ.get("MFN_BACK_PRIO", "-1")))
         self._comm_stream_ptr = ctypes.c_void_p(self._comm_stream.cuda_stream)
         self._comm_done = torch.cuda.Event()
         self._comm_pending = False
