@@ -8,11 +8,13 @@
 // reference's sequential fp32 accumulation only to rounding (tolerance stated in tests/).
 // Algorithmic bytes: fw 28 B/sample + 52 B/ray, bw 48 B/sample + 64 B/ray.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/mfnerf_b200.h"
 
 namespace mfn {
 
 constexpr int kCompWarps = 8;
+constexpr int kCompLossWarps = 4;      // default CTA size of composite_loss_train_kernel, in rays
 
 // alpha exactly as the reference computes it: 1 - __expf(-sigma*delta)  (volumerendering.cu:30)
 __device__ __forceinline__ float alpha_of(float sigma, float delta) { return __fadd_rn(1.0f, -__expf(-__fmul_rn(sigma, delta))); }
@@ -179,7 +181,8 @@ composite_loss_train_kernel(const float* __restrict__ sigmas, const float* __res
     __shared__ __align__(16) float s_om[kCompWarps][32];
     __shared__ float s_loss[kCompWarps][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * kCompWarps + warp;
+    const int n_warps = (int)(blockDim.x >> 5);      // rays per CTA: a CTA keeps its SM slots until its LONGEST ray is done (barrier below)
+    const int64_t row = (int64_t)blockIdx.x * n_warps + warp;
     float l_rgb = 0.f, l_op = 0.f;
     if (row < n_rows) {
         const int64_t ray = rays_a[3 * row], start = rays_a[3 * row + 1];
@@ -281,7 +284,7 @@ composite_loss_train_kernel(const float* __restrict__ sigmas, const float* __res
     if (threadIdx.x == 0) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < kCompWarps; ++k) { a0 += s_loss[k][0]; a1 += s_loss[k][1]; }
+        for (int k = 0; k < n_warps; ++k) { a0 += s_loss[k][0]; a1 += s_loss[k][1]; }
         atomicAdd(scratch, a0); atomicAdd(scratch + 1, a1);
         __threadfence();
         unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 2);
@@ -380,7 +383,9 @@ extern "C" int mfn_composite_loss_train(const float* sigmas, const float* rgbs, 
         set_error("mfn_composite_loss_train: null pointer"); return MFN_ERR_ARG;
     }
     ProfScope ps("composite_loss_train", (cudaStream_t)stream);
-    composite_loss_train_kernel<<<(int)ceil_div(n_rays, kCompWarps), kCompWarps * 32, 0, (cudaStream_t)stream>>>(
+    static int cw = 0;      // rays (warps) per CTA of the fused kernel; measured on B200 (8192 rays): see DESIGN.md
+    if (cw == 0) { const char* e = getenv("MFN_COMP_WARPS"); cw = e ? atoi(e) : kCompLossWarps; if (cw < 1 || cw > kCompWarps) cw = kCompLossWarps; }
+    composite_loss_train_kernel<<<(int)ceil_div(n_rays, cw), cw * 32, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, target, T_threshold, n_rays, bg_rgb_host[0], bg_rgb_host[1], bg_rgb_host[2], lambda_opacity, grad_scale,
         total_samples, opacity, depth, rgb, ws, rgb_final, dL_drgb, dL_dopacity, dL_dsigmas, dL_drgbs, loss_out, scratch16, clear_flag);
     return check_launch("mfn_composite_loss_train", (cudaStream_t)stream);

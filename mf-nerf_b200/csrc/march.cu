@@ -152,13 +152,21 @@ march_scan_write_kernel(const float* __restrict__ rays_o, const float* __restric
     const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
     const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
     const float2* my = stash + r * (int64_t)max_samples;
-    for (int s = lane; s < n; s += 32) {
-        const int64_t o = start + s;
-        if (o >= capacity) break;
-        const float2 td = my[s];
-        xyzs[3 * o] = __fmaf_rn(dx, td.x, ox); xyzs[3 * o + 1] = __fmaf_rn(dy, td.x, oy); xyzs[3 * o + 2] = __fmaf_rn(dz, td.x, oz);
-        dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
-        ts[o] = td.x; deltas[o] = td.y;
+    // four stash loads in flight per lane: the kernel's duration is its longest ray's chain of (load -> stores) rounds
+    for (int s0 = lane; s0 < n; s0 += 128) {
+        float2 td[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int s = s0 + 32 * u; td[u] = s < n ? my[s] : make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + 32 * u;
+            const int64_t o = start + s;
+            if (s < n && o < capacity) {
+                xyzs[3 * o] = __fmaf_rn(dx, td[u].x, ox); xyzs[3 * o + 1] = __fmaf_rn(dy, td[u].x, oy); xyzs[3 * o + 2] = __fmaf_rn(dz, td[u].x, oz);
+                dirs[3 * o] = dx; dirs[3 * o + 1] = dy; dirs[3 * o + 2] = dz;
+                ts[o] = td[u].x; deltas[o] = td[u].y;
+            }
+        }
     }
 }
 

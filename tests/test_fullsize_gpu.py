@@ -173,9 +173,13 @@ def test_render_full_frame_wavefront_equals_per_op_loop():
     assert int(a["total_samples"]) == int(b["total_samples"]) > 640_000
     for k in ("opacity", "depth", "rgb"):
         torch.testing.assert_close(a[k], b[k], rtol=0, atol=1e-6)
-    c = eng.render(ro, rd, min_chunk=8)       # a coarser schedule changes the iteration count, not the image
+    # A coarser schedule (at least 8 samples per ray and iteration) changes the iteration count, not the per-sample arithmetic; what it
+    # can change is WHERE the reference's sample budget (rendering.py:69, `while samples < max_samples`, samples += N_samples) cuts off the
+    # few rays that are still alive at the end: their last low-weight samples -- hence 1e-5 here, against 1e-6 for the reference schedule
+    c = eng.render(ro, rd, min_chunk=8)
     for k in ("opacity", "depth", "rgb"):
-        torch.testing.assert_close(c[k], b[k], rtol=0, atol=1e-6)
+        torch.testing.assert_close(c[k], b[k], rtol=0, atol=1e-5)
+        assert int(((c[k] - b[k]).abs() > 1e-6).sum()) <= 64
     assert c["iterations"] < a["iterations"]
     assert float(a["opacity"].min()) >= 0 and float(a["opacity"].max()) <= 1 + 1e-5
 
