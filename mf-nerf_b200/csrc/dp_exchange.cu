@@ -57,11 +57,13 @@ dp_exchange_adam_kernel(const PeerPtrs grads, const PeerPtrs shadow, const PeerP
                         float beta1, float beta2, float eps, const float* __restrict__ amp, int32_t* __restrict__ skip_out) {
     // one thread per CTA reads the ranks' overflow flags (every thread doing so put 300 k uncached loads of ONE peer address on the links:
     // that, not the data, was most of the first version's 194 us)
+    // (lane r of warp 0 reads rank r's flag: the N peer round trips overlap instead of queueing behind each other)
     __shared__ int s_bad;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         int bad = 0;
-        for (int r = 0; r < world; ++r) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
-        s_bad = bad;
+        for (int r = (int)threadIdx.x; r < world; r += 32) bad |= *reinterpret_cast<const volatile int32_t*>(flags.p[r]);
+        bad = __any_sync(0xffffffffu, bad != 0);
+        if (threadIdx.x == 0) s_bad = bad;
     }
     __syncthreads();
     const bool skip = s_bad != 0;

@@ -115,10 +115,11 @@ class SymmetricBuffers:
         base = [int(p) for p in self.hdl.buffer_ptrs]
         arr = lambda off: (ctypes.c_uint64 * world)(*[b + off for b in base])
         self.grads_ptrs, self.shadow_ptrs, self.flag_ptrs = arr(off_g), arr(off_s), arr(off_f)
-        # NVSwitch multicast (multimem.ld_reduce / multimem.st) pays from 4 ranks on; between 2 GPUs the in-fabric reduction is slower than
-        # two peer loads (measured on 2 x B200, 11.4 M parameters: 192 us vs 89 us).  MFN_DP_MULTICAST=1 / 0 forces the choice.
-        want = os.environ.get("MFN_DP_MULTICAST", "auto")
-        use_mc = getattr(self.hdl, "has_multicast_support", False) and (want == "1" or (want == "auto" and world >= 4))
+        # NVSwitch multicast (multimem.ld_reduce / multimem.st) is opt-in (MFN_DP_MULTICAST=1): measured on B200 with 11.4 M parameters the
+        # in-fabric reduction costs ~175-200 us whatever the number of ranks, the peer-load path 93 us (2 GPUs), 114 us (4), 183 us (8) --
+        # and at 8 GPUs, where the two kernels tie, the step with peer loads is still the shorter one (0.485 vs 0.495 ms).
+        want = os.environ.get("MFN_DP_MULTICAST", "0")
+        use_mc = getattr(self.hdl, "has_multicast_support", False) and want == "1"
         mc = int(self.hdl.multicast_ptr) if use_mc else 0
         self.grads_mc, self.shadow_mc = (mc + off_g, mc + off_s) if mc else (0, 0)
         self.multicast = bool(mc)

@@ -695,7 +695,10 @@ class NGPEngine:
                      self._rank * self._shard, self._shard, ptr(self._adam_hyper), 0.9, 0.999, 1e-15, ptr(self._amp), ptr(self._skip), self._comm_stream_ptr)
                 call("mfn_amp_update", ptr(self._amp), ptr(self._skip), *self._amp_rule, 0.9, 0.999, self._comm_stream_ptr)
                 sy.barrier(1)                  # every rank's shadow stores are visible and every rank has read this rank's gradients
-                self.grads.zero_()             # (local HBM; clearing all copies from the shard owner doubles the NVLink store traffic)
+                self._comm_done.record(cs)     # the next step's field forward waits for the barrier, not for the gradient clear behind it:
+                self.grads.zero_()             # local HBM (clearing all copies from the shard owner doubles the NVLink store traffic), and
+                self._comm_pending = True      # stream-ordered before the next backward pass, the first kernel to touch the buffer again
+                return
             elif self.collectives:
                 self._back_done.record(cs); self._back_pending = True
                 torch.distributed.reduce_scatter_tensor(self._grad_shard, self.grads, op=torch.distributed.ReduceOp.SUM, group=self.pg)
