@@ -41,7 +41,7 @@ print("  exit time by SM (sorted):", " ".join(f"{v:.0f}" for v in np.sort(np.arr
 print("samples of the last step", int(eng.counter[0].item()))
 
 # backward kernel: stamps after every MMA-completion wait ("w") and every barrier ("s") of CTA 0 / thread 0
-b = dbg.cpu()[256:].view(6, 40).numpy()
+b = dbg.cpu()[256:496].view(6, 40).numpy()
 print("backward kernel, cycles between consecutive stamps (tile start, load+sync, then wait/sync per stage):")
 for k in range(6):
     r = [int(v) for v in b[k] if v != 0]
