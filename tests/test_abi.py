@@ -46,7 +46,7 @@ def test_render_and_field_entry_points_validate_arguments():
     from mfnerf_b200 import _lib
     from mfnerf_b200.engine import make_field_cfg
     lib = _lib.lib
-    assert lib.mfn_render_workspace_bytes(640000, 1) >= 640000 * (8 + 8 + 4 + 48)   # hits_t, 2 alive lists, N_eff + 48 B per sample row
+    assert lib.mfn_render_workspace_bytes(640000, 1) >= 640000 * (8 + 8 + 4 + 24)   # hits_t, 2 alive lists, N_eff + 24 B per sample row (t, dt, sigma, rgb)
     assert lib.mfn_render_workspace_bytes(-1, 1) == -1 and lib.mfn_render_workspace_bytes(10, 0) == -1
     assert lib.mfn_render_begin(None, None, None, None, 16, 0.01, 1, 1024, None, None, None, None, 0, None) == -2
     assert b"mfn_render_begin" in lib.mfn_last_error()
