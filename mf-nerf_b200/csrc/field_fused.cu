@@ -902,7 +902,8 @@ static int launch_bwd(const FusedArgs& a, cudaStream_t st) {
     static bool once = (cudaFuncSetAttribute(field_bwd_fused_kernel<NH2, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<RW>::BwdSmem), true);
     (void)once;
     const int64_t tiles = ceil_div(a.n_max, kFT);
-    const int64_t cap = bwd_max_ctas(RW);
+    int64_t cap = bwd_max_ctas(RW);
+    { static const char* e = getenv("MFN_BWD_CTAS"); if (e && atoi(e) > 0 && atoi(e) < cap) cap = atoi(e); }      // (experiments: chains per SM)
     const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
     field_bwd_fused_kernel<NH2, RW><<<grid, kBwdThreads, Lay<RW>::BwdSmem, st>>>(a);
     return (int)grid;
