@@ -192,6 +192,11 @@ __device__ __forceinline__ void pack16(const uint32_t (&r)[16], uint4& o0, uint4
     o1.z = pack2(__uint_as_float(r[12]), __uint_as_float(r[13])); o1.w = pack2(__uint_as_float(r[14]), __uint_as_float(r[15]));
 }
 
+__device__ __forceinline__ uint32_t relu2(uint32_t packed) {
+    const __half2 z = __float2half2_rn(0.f);
+    const __half2 v = __hmax2(*reinterpret_cast<const __half2*>(&packed), z);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
 // TMEM (32 fp32 columns starting at col0) -> ReLU -> fp16 -> columns col0..col0+31 of row `row` of a [128 x C] row-core tile
 // (16 columns per tcgen05.ld: the 64-wide forward kernel lives on 48 registers to fit 5 CTAs per SM)
 template <int C>
@@ -202,12 +207,12 @@ __device__ __forceinline__ void relu_epilogue32(uint32_t taddr, unsigned char* t
         tmem_ld_x16(taddr + col0 + 16 * h, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 2; ++c) {      // round first, clamp the PAIR afterwards: fp16(max(x, 0)) == max(fp16(x), 0) (rounding is monotone, max(-0, +0) = +0)
             uint4 o;
-            o.x = pack2(fmaxf(__uint_as_float(r[8 * c + 0]), 0.f), fmaxf(__uint_as_float(r[8 * c + 1]), 0.f));
-            o.y = pack2(fmaxf(__uint_as_float(r[8 * c + 2]), 0.f), fmaxf(__uint_as_float(r[8 * c + 3]), 0.f));
-            o.z = pack2(fmaxf(__uint_as_float(r[8 * c + 4]), 0.f), fmaxf(__uint_as_float(r[8 * c + 5]), 0.f));
-            o.w = pack2(fmaxf(__uint_as_float(r[8 * c + 6]), 0.f), fmaxf(__uint_as_float(r[8 * c + 7]), 0.f));
+            o.x = relu2(pack2(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1])));
+            o.y = relu2(pack2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])));
+            o.z = relu2(pack2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])));
+            o.w = relu2(pack2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])));
             *reinterpret_cast<uint4*>(tile + tile_off(row, col0 + 16 * h + c * 8, C)) = o;
         }
     }
@@ -542,12 +547,11 @@ __device__ __forceinline__ void mask_epilogue(uint32_t taddr, unsigned char* til
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint4 act = *reinterpret_cast<const uint4*>(tile + tile_off(row, col0 + c * 8, C));
-            const __half2* ah = reinterpret_cast<const __half2*>(&act);
+            const uint32_t* aw = &act.x;
             uint32_t* ow = &o[q][c].x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 av = __half22float2(ah[k]);
-                ow[k] = pack2(av.x > 0.f ? __uint_as_float(r[8 * c + 2 * k]) : 0.f, av.y > 0.f ? __uint_as_float(r[8 * c + 2 * k + 1]) : 0.f);
+            for (int k = 0; k < 4; ++k) {      // the activations are ReLU outputs (>= +0): "> 0" is "bits != 0", no conversion needed
+                ow[k] = pack2((aw[k] & 0xffffu) ? __uint_as_float(r[8 * c + 2 * k]) : 0.f, (aw[k] >> 16) ? __uint_as_float(r[8 * c + 2 * k + 1]) : 0.f);
             }
         }
     }
