@@ -3,10 +3,11 @@
 //
 // Here every rank owns the shard [shard_begin, shard_begin + n) of the flat parameter vector (ZeRO-1 style) and ONE kernel per rank does,
 // element by element of its shard:
-//     g      = sum over ranks of grads_r[j]            one multimem.ld_reduce (the NVSwitch adds the N copies in the fabric: 1/N of the
-//                                                      gradient bytes cross this GPU's links) -- or N peer loads when there is no multicast
+//     g      = sum over ranks of grads_r[j]            N peer loads summed in rank order (the default: measured faster at 2, 4 and 8 B200s,
+//                                                      DESIGN.md section 6) -- or one multimem.ld_reduce when the caller passes the multicast
+//                                                      addresses (the NVSwitch adds the N copies in the fabric)
 //     Adam on the fp32 master copy (local HBM: p, m, v of the shard only), unscale and skip-on-overflow like optim.cu
-//     shadow_r[j] <- fp16(p) on every rank             one multimem.st: the fp16 parameters every field kernel gathers from
+//     shadow_r[j] <- fp16(p) on every rank             N peer stores (or one multimem.st): the fp16 parameters every field kernel gathers from
 // i.e. reduce-scatter + optimiser + all-gather in one pass, 4 + 2 bytes per parameter over the links instead of NCCL's three collectives
 // with the optimiser in between (every rank clears its own gradient buffer locally after the closing barrier: clearing all copies from
 // the owner -- tried first -- doubles the store traffic on the links).  The overflow flags of all ranks are OR-ed by every CTA (N loads) so that

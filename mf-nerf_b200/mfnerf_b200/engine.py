@@ -79,7 +79,7 @@ class NGPEngine:
         _init_mlp(p[self.off_rgb:self.off_rgb + self.n_rgb], 32, rgb_channels, rgb_layers, 16, g)
         self.params = p.to(d)
         # Data-parallel: gradients, fp16 shadow parameters and the overflow flag live in ONE symmetric-memory allocation (peer-mapped on
-        # every rank, NVSwitch multicast where available) so that the gradient exchange + optimiser is one kernel over NVLink
+        # every rank; its NVSwitch multicast address is used on request only) so that the gradient exchange + optimiser is one kernel over NVLink
         # (csrc/dp_exchange.cu).  MFN_DP_EXCHANGE=nccl keeps the three NCCL collectives (A/B measurements, fabrics without P2P).
         self._symm = None
         if world_size > 1 and os.environ.get("MFN_DP_EXCHANGE", "fused") == "fused":
